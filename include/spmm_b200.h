@@ -1,0 +1,199 @@
+/*
+ * spmm_b200.h — C ABI of the B200-native fp32 CSR SpMM engine (libspmm_b200.so).
+ *
+ * This is the drop-in boundary for the reference's SpMM hot path.  Every entry
+ * point takes plain pointers and sizes (no torch types); device pointers are
+ * what the reference's pybind layer extracts with data_ptr<T>() before it calls
+ * its own wrappers.  Citations are relative to the reference tree
+ * (smoorjani/matrix-multiplication):
+ *
+ *   b200_spmm_csr_forward      replaces cusparse_mm_wrapper      src/baseline_mm.cu:167-216
+ *                              and      naive_spmm_wrapper       src/naive_sparse_mm.cu:104-136
+ *                              (bound as custom_mm.cusparse_mmul src/custom_mm.cpp:203-217,
+ *                               custom_mm.naive_spmm             src/custom_mm.cpp:166-179)
+ *   b200_dense_to_csr_*        replaces dense_to_csr / free_csr  src/baseline_mm.cu:218-270
+ *   b200_csr_transpose         replaces m1.transpose().to_sparse_csr()   matmuls.py:253
+ *   b200_sddmm_csr             replaces the dense grad_m1 product        matmuls.py:250
+ *   b200_plan_*                replaces the layer-keyed inspect/execute/clean registries
+ *                              src/custom_mm.cpp:236-281 (cusparse_*) and :293-357 (tiledspmm_*)
+ *
+ * Conventions (same as the reference, src/custom_mm.cpp:203-217):
+ *   - fp32 values, int32 indices, index base 0, CSR with sorted rows;
+ *   - dense matrices are ROW-MAJOR with an explicit leading dimension in elements;
+ *   - C is fully overwritten (alpha = 1, beta = 0), empty rows produce zeros;
+ *   - the caller owns every buffer; the library only borrows pointers for the call
+ *     (a plan borrows the CSR arrays until b200_plan_destroy);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     device entry points never synchronise the stream unless documented.
+ *
+ * Error behaviour: every function returns 0 on success and a non-zero
+ * b200_status otherwise; b200_last_error() returns a thread-local message.
+ * (The reference throws std::logic_error on CUDA failures, src/Utilities.cuh:17-22,
+ *  and silently prints cuSPARSE failures, :145-154; here every failure is reported.)
+ */
+#ifndef SPMM_B200_H_
+#define SPMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = 1,   /* bad argument (null pointer, negative size, ld < N, ...) */
+  B200_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed            */
+  B200_ERR_NO_DEVICE = 3, /* no sm_100 device available                             */
+  B200_ERR_ALLOC = 4      /* device or host allocation failed                       */
+} b200_status;
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* b200_last_error(void);
+
+/* Library/ABI version (bumped when a signature changes) and build info string. */
+int b200_abi_version(void);
+const char* b200_build_info(void);
+
+/* Number of SpMM-engine kernels launched by this process so far (all threads). */
+uint64_t b200_kernel_launch_count(void);
+
+/* Launches one empty kernel on `stream`, waits for it and returns the SM count:
+ * "is there a usable sm_100 device" (stands in for the reference's dummy_kernel,
+ * src/baseline_mm.cu:24-35, and for cusparseCreate in init_cusparse). */
+int b200_smoke_kernel(void* stream, int* sm_count);
+
+/* ---- tuning knobs (process-wide; for benchmarks and tests) ------------------
+ * stage_mode: 0 = col/val read straight from global memory,
+ *             1 = col/val segments staged in shared memory with TMA bulk copies
+ *                 (cp.async.bulk + mbarrier); default 1.
+ * items_per_task: merge-path items (row ends + non-zeros) per warp task; 0 = auto. */
+int b200_set_option(const char* name, int64_t value);
+int64_t b200_get_option(const char* name);
+
+/* ---- workspace sizing --------------------------------------------------------
+ * Bytes of device scratch b200_spmm_csr_forward needs for a matrix with M rows,
+ * nnz non-zeros and N dense columns (partial sums of rows split across tasks). */
+size_t b200_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t N);
+
+/* ---- forward: C[M,N] = A_csr[M,K] * B[K,N] ------------------------------------
+ * All pointers are DEVICE pointers.  workspace may be NULL (then the library
+ * uses a cached per-device scratch buffer grown on demand, stream-ordered). */
+int b200_spmm_csr_forward(const int32_t* d_row_ptr, const int32_t* d_col_ind,
+                          const float* d_val, int64_t M, int64_t K, int64_t nnz,
+                          const float* d_B, int64_t ldb, int64_t N,
+                          float* d_C, int64_t ldc,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Same, with per-call flags (B200_FLAG_NO_STAGE: read col/val straight from global
+ * memory instead of staging them in shared memory with TMA bulk copies). */
+#define B200_FLAG_NO_STAGE 1u
+int b200_spmm_csr_forward_flags(const int32_t* d_row_ptr, const int32_t* d_col_ind,
+                                const float* d_val, int64_t M, int64_t K, int64_t nnz,
+                                const float* d_B, int64_t ldb, int64_t N,
+                                float* d_C, int64_t ldc,
+                                void* d_workspace, size_t workspace_bytes, void* stream,
+                                uint32_t flags);
+
+/* ---- SDDMM on A's pattern: out_val[p] = sum_j G[row(p), j] * B[col(p), j] ------
+ * grad_A of C = A*B restricted to A's non-zeros (matmuls.py:250, intended formula
+ * grad_C * B^T sampled at the pattern).  G is [M,N] (ldg), B is [K,N] (ldb). */
+int b200_sddmm_csr(const int32_t* d_row_ptr, const int32_t* d_col_ind,
+                   int64_t M, int64_t K, int64_t nnz,
+                   const float* d_G, int64_t ldg, const float* d_B, int64_t ldb, int64_t N,
+                   float* d_out_val, void* stream);
+
+/* ---- CSR transpose (CSR of A^T, i.e. CSC of A), rows sorted, stable ------------
+ * Outputs: t_row_ptr[K+1], t_col_ind[nnz] (original row ids), t_val[nnz], and
+ * optionally t_perm[nnz] (t_val[q] = val[t_perm[q]]; may be NULL).
+ * d_val may be NULL (pattern only; then t_val is ignored).
+ * Synchronises `stream` internally only for temporary allocation bookkeeping. */
+int b200_csr_transpose(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val,
+                       int64_t M, int64_t K, int64_t nnz,
+                       int32_t* d_t_row_ptr, int32_t* d_t_col_ind, float* d_t_val,
+                       int32_t* d_t_perm, void* stream);
+
+/* Re-gather values through a transpose permutation: dst[q] = src[perm[q]]. */
+int b200_gather_f32(const float* d_src, const int32_t* d_perm, int64_t n, float* d_dst, void* stream);
+
+/* ---- dense -> CSR, bit-exact with the reference's construction ----------------
+ * Keeps x != 0.0f (NaN kept, -0.0 dropped), row-major order, int32 indices.
+ * Two-phase like cusparseDenseToSparse_analysis/_convert (src/baseline_mm.cu:241-258):
+ *   count: writes d_row_ptr[M+1] (exclusive scan, row_ptr[M] = nnz) and, if
+ *          h_nnz != NULL, synchronises the stream and returns nnz on the host;
+ *   fill : writes d_col_ind[nnz], d_val[nnz] for a row_ptr produced by count. */
+int b200_dense_to_csr_count(const float* d_dense, int64_t M, int64_t K, int64_t ld,
+                            int32_t* d_row_ptr, int64_t* h_nnz, void* stream);
+int b200_dense_to_csr_fill(const float* d_dense, int64_t M, int64_t K, int64_t ld,
+                           const int32_t* d_row_ptr, int32_t* d_col_ind, float* d_val,
+                           void* stream);
+/* One-call variant with the reference's ownership (dense_to_csr allocates with
+ * cudaMalloc, free_csr releases; src/baseline_mm.cu:218-270). Synchronises. */
+int b200_dense_to_csr_alloc(const float* d_dense, int64_t M, int64_t K, int64_t ld,
+                            float** d_val, int32_t** d_col_ind, int32_t** d_row_ptr,
+                            int64_t* nnz, void* stream);
+int b200_free_csr(float* d_val, int32_t* d_col_ind, int32_t* d_row_ptr);
+
+/* ---- plans: the inspect / execute / clean triple -------------------------------
+ * A plan borrows a device CSR, owns its scratch, and lazily builds + caches the
+ * transposed CSR used by backward_B.  Not thread-safe per plan. */
+typedef struct b200_plan b200_plan;
+
+int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val,
+                     int64_t M, int64_t K, int64_t nnz, b200_plan** out_plan, void* stream);
+int b200_plan_destroy(b200_plan* plan);
+/* Tell the plan that d_val changed in place (pattern unchanged): the cached
+ * transposed values are re-gathered on next use. */
+int b200_plan_values_updated(b200_plan* plan);
+/* max row length, number of empty rows (computed at creation). */
+int b200_plan_stats(const b200_plan* plan, int64_t* max_row_nnz, int64_t* empty_rows);
+
+int b200_plan_forward(b200_plan* plan, const float* d_B, int64_t ldb, int64_t N,
+                      float* d_C, int64_t ldc, void* stream);
+/* grad_B[K,N] = A^T * G[M,N]  — SpMM over the cached transposed CSR (matmuls.py:253). */
+int b200_plan_backward_B(b200_plan* plan, const float* d_G, int64_t ldg, int64_t N,
+                         float* d_dB, int64_t lddb, void* stream);
+/* grad_A values on A's pattern (SDDMM). */
+int b200_plan_backward_A(b200_plan* plan, const float* d_G, int64_t ldg,
+                         const float* d_B, int64_t ldb, int64_t N,
+                         float* d_dval, void* stream);
+
+/* ---- host-buffer convenience entry points (end-to-end path) --------------------
+ * All pointers are HOST pointers (pinned memory makes the copies asynchronous).
+ * Each call copies its inputs to the device, runs the device path above and
+ * copies the result back; it returns after the result is in host memory. */
+int b200_spmm_csr_forward_host(const int32_t* h_row_ptr, const int32_t* h_col_ind,
+                               const float* h_val, int64_t M, int64_t K, int64_t nnz,
+                               const float* h_B, int64_t N, float* h_C);
+int b200_sddmm_csr_host(const int32_t* h_row_ptr, const int32_t* h_col_ind,
+                        int64_t M, int64_t K, int64_t nnz,
+                        const float* h_G, const float* h_B, int64_t N, float* h_out_val);
+int b200_spmm_csr_backward_B_host(const int32_t* h_row_ptr, const int32_t* h_col_ind,
+                                  const float* h_val, int64_t M, int64_t K, int64_t nnz,
+                                  const float* h_G, int64_t N, float* h_dB);
+int b200_csr_transpose_host(const int32_t* h_row_ptr, const int32_t* h_col_ind, const float* h_val,
+                            int64_t M, int64_t K, int64_t nnz,
+                            int32_t* h_t_row_ptr, int32_t* h_t_col_ind, float* h_t_val);
+/* Returns nnz through *nnz; h_col_ind/h_val must hold capacity elements
+ * (B200_ERR_INVALID with *nnz set if capacity is too small; pass capacity 0 to query). */
+int b200_dense_to_csr_host(const float* h_dense, int64_t M, int64_t K,
+                           int32_t* h_row_ptr, int32_t* h_col_ind, float* h_val,
+                           int64_t capacity, int64_t* nnz);
+
+/* ---- host-side partition helpers (pure CPU; used by planners and tests) --------
+ * Merge-path task boundary for diagonal d over (row ends, non-zeros):
+ * returns the (row, nnz offset) a task starting at item d begins with, snapped to
+ * the row start unless the row is longer than heavy_threshold. */
+int b200_merge_path_boundary(const int32_t* h_row_ptr, int64_t M, int64_t nnz,
+                             int64_t d, int64_t heavy_threshold,
+                             int64_t* row, int64_t* nz);
+/* nnz-balanced contiguous row shards: shard g owns rows [bounds[g], bounds[g+1]).
+ * cost(row range) = nnz * nnz_weight + rows * row_weight (row_weight ~ N for C writes). */
+int b200_shard_rows(const int32_t* h_row_ptr, int64_t M, int parts,
+                    double nnz_weight, double row_weight, int64_t* bounds /* parts+1 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMM_B200_H_ */

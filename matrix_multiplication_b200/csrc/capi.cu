@@ -1,0 +1,577 @@
+// capi.cu — the extern "C" surface declared in include/spmm_b200.h: argument checks,
+// plans (inspect / execute / clean), host-buffer entry points, options and errors.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char tl_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+
+Options& options() {
+  static Options o;
+  return o;
+}
+
+int device_sm_count() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+// per-device scratch, grown on demand
+static std::mutex g_scratch_mu;
+static void* g_scratch[64] = {nullptr};
+static size_t g_scratch_bytes[64] = {0};
+
+int get_scratch(size_t bytes, void** ptr) {
+  int dev = 0;
+  B200_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  if (g_scratch_bytes[dev] < bytes) {
+    if (g_scratch[dev]) {
+      B200_CUDA_OK(cudaDeviceSynchronize());
+      B200_CUDA_OK(cudaFree(g_scratch[dev]));
+      g_scratch[dev] = nullptr;
+      g_scratch_bytes[dev] = 0;
+    }
+    size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
+    if (cudaMalloc(&g_scratch[dev], want) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc of %zu scratch bytes failed", want);
+      return B200_ERR_ALLOC;
+    }
+    g_scratch_bytes[dev] = want;
+  }
+  *ptr = g_scratch[dev];
+  return B200_OK;
+}
+
+static int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: the SpMM engine has no CPU fallback");
+    return B200_ERR_NO_DEVICE;
+  }
+  return B200_OK;
+}
+
+static int check_csr_dims(int64_t M, int64_t K, int64_t nnz) {
+  B200_REQUIRE(M >= 0 && K >= 0 && nnz >= 0, "negative dimension");
+  B200_REQUIRE(M < 0x7fffffffLL && K < 0x7fffffffLL && nnz < 0x7fffffffLL, "int32 index range exceeded");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_plan {
+  const int* row_ptr;
+  const int* col;
+  const float* val;
+  int M, K, nnz;
+  int max_row, empty_rows;
+  // cached transposed CSR (owned)
+  int* t_row_ptr = nullptr;
+  int* t_col = nullptr;
+  float* t_val = nullptr;
+  int* t_perm = nullptr;
+  bool t_built = false;
+  bool t_val_stale = false;
+  // owned scratch for forward / backward_B
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+static int plan_ensure_ws(b200_plan* p, size_t need) {
+  if (p->ws_bytes >= need) return B200_OK;
+  if (p->ws) {
+    B200_CUDA_OK(cudaDeviceSynchronize());
+    B200_CUDA_OK(cudaFree(p->ws));
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+  }
+  if (cudaMalloc(&p->ws, need) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc of %zu plan workspace bytes failed", need);
+    return B200_ERR_ALLOC;
+  }
+  p->ws_bytes = need;
+  return B200_OK;
+}
+
+static int plan_ensure_transpose(b200_plan* p, cudaStream_t s) {
+  if (!p->t_built) {
+    B200_CUDA_OK(cudaMalloc(&p->t_row_ptr, ((size_t)p->K + 1) * sizeof(int)));
+    const size_t n = std::max<size_t>((size_t)p->nnz, 1);
+    B200_CUDA_OK(cudaMalloc(&p->t_col, n * sizeof(int)));
+    B200_CUDA_OK(cudaMalloc(&p->t_val, n * sizeof(float)));
+    B200_CUDA_OK(cudaMalloc(&p->t_perm, n * sizeof(int)));
+    int rc = launch_transpose(p->row_ptr, p->col, p->val, p->M, p->K, p->nnz, p->t_row_ptr, p->t_col,
+                              p->t_val, p->t_perm, s);
+    if (rc != B200_OK) return rc;
+    p->t_built = true;
+    p->t_val_stale = false;
+  } else if (p->t_val_stale) {
+    int rc = launch_gather(p->val, p->t_perm, p->nnz, p->t_val, s);
+    if (rc != B200_OK) return rc;
+    p->t_val_stale = false;
+  }
+  return B200_OK;
+}
+
+namespace {
+__global__ void smoke_kernel() {}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc of %zu bytes failed", bytes);
+      return B200_ERR_ALLOC;
+    }
+    return B200_OK;
+  }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+#define H2D(dst, src, bytes, s) \
+  do { if ((bytes) > 0) B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s)); } while (0)
+#define D2H(dst, src, bytes, s) \
+  do { if ((bytes) > 0) B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); } while (0)
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* b200_last_error(void) { return tl_error; }
+int b200_abi_version(void) { return 1; }
+const char* b200_build_info(void) {
+  return "spmm_b200 sm_100a fp32 CSR SpMM engine (merge-path tasks, TMA-staged col/val), built " __DATE__;
+}
+uint64_t b200_kernel_launch_count(void) { return g_launches.load(); }
+
+int b200_smoke_kernel(void* stream, int* sm_count) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  smoke_kernel<<<1, 32, 0, s>>>();
+  B200_LAUNCH_OK("smoke_kernel");
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  if (sm_count) *sm_count = device_sm_count();
+  return B200_OK;
+}
+
+int b200_set_option(const char* name, int64_t value) {
+  B200_REQUIRE(name != nullptr, "option name");
+  if (!strcmp(name, "stage_mode")) { options().stage_mode = (int)value; return B200_OK; }
+  if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
+  if (!strcmp(name, "batch")) { options().batch = (int)value; return B200_OK; }
+  set_error("unknown option '%s'", name);
+  return B200_ERR_INVALID;
+}
+int64_t b200_get_option(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "stage_mode")) return options().stage_mode;
+  if (!strcmp(name, "items_per_task")) return options().items_per_task;
+  if (!strcmp(name, "batch")) return options().batch;
+  return -1;
+}
+
+size_t b200_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t N) {
+  if (M < 0 || nnz < 0 || N < 0) return 0;
+  return fwd_workspace_bytes(M, nnz, N);
+}
+
+int b200_spmm_csr_forward(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val,
+                          int64_t M, int64_t K, int64_t nnz, const float* d_B, int64_t ldb, int64_t N,
+                          float* d_C, int64_t ldc, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+  return b200_spmm_csr_forward_flags(d_row_ptr, d_col_ind, d_val, M, K, nnz, d_B, ldb, N, d_C, ldc,
+                                     d_workspace, workspace_bytes, stream, 0u);
+}
+
+int b200_spmm_csr_forward_flags(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val,
+                                int64_t M, int64_t K, int64_t nnz, const float* d_B, int64_t ldb,
+                                int64_t N, float* d_C, int64_t ldc, void* d_workspace,
+                                size_t workspace_bytes, void* stream, uint32_t flags) {
+  int rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  B200_REQUIRE(ldb >= N && ldc >= N, "leading dimension smaller than N");
+  if (M == 0 || N == 0) return B200_OK;
+  B200_REQUIRE(d_row_ptr != nullptr && d_C != nullptr, "null row_ptr / C");
+  B200_REQUIRE(nnz == 0 || (d_col_ind != nullptr && d_val != nullptr && d_B != nullptr), "null col/val/B");
+  FwdParams p{};
+  p.row_ptr = d_row_ptr; p.col = d_col_ind; p.val = d_val;
+  p.M = (int)M; p.nnz = (int)nnz;
+  p.B = d_B; p.ldb = ldb; p.N = (int)N; p.C = d_C; p.ldc = ldc;
+  p.stage = (flags & B200_FLAG_NO_STAGE) ? 0 : -1;
+  return launch_spmm_forward(p, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200_sddmm_csr(const int32_t* d_row_ptr, const int32_t* d_col_ind, int64_t M, int64_t K, int64_t nnz,
+                   const float* d_G, int64_t ldg, const float* d_B, int64_t ldb, int64_t N,
+                   float* d_out_val, void* stream) {
+  int rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  B200_REQUIRE(ldg >= N && ldb >= N, "leading dimension smaller than N");
+  if (nnz == 0) return B200_OK;
+  B200_REQUIRE(d_row_ptr && d_col_ind && d_out_val, "null CSR / output pointer");
+  B200_REQUIRE(N == 0 || (d_G && d_B), "null G / B");
+  return launch_sddmm(d_row_ptr, d_col_ind, (int)M, (int)nnz, d_G, ldg, d_B, ldb, (int)N, d_out_val,
+                      (cudaStream_t)stream);
+}
+
+int b200_csr_transpose(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val, int64_t M,
+                       int64_t K, int64_t nnz, int32_t* d_t_row_ptr, int32_t* d_t_col_ind,
+                       float* d_t_val, int32_t* d_t_perm, void* stream) {
+  int rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(d_t_row_ptr != nullptr, "null output row_ptr");
+  B200_REQUIRE(nnz == 0 || (d_row_ptr && d_col_ind && d_t_col_ind), "null CSR pointer");
+  B200_REQUIRE(d_val == nullptr || nnz == 0 || d_t_val != nullptr, "null output values");
+  return launch_transpose(d_row_ptr, d_col_ind, d_val, (int)M, (int)K, (int)nnz, d_t_row_ptr,
+                          d_t_col_ind, d_t_val, d_t_perm, (cudaStream_t)stream);
+}
+
+int b200_gather_f32(const float* d_src, const int32_t* d_perm, int64_t n, float* d_dst, void* stream) {
+  B200_REQUIRE(n >= 0, "negative length");
+  if (n == 0) return B200_OK;
+  B200_REQUIRE(d_src && d_perm && d_dst, "null pointer");
+  return launch_gather(d_src, d_perm, n, d_dst, (cudaStream_t)stream);
+}
+
+int b200_dense_to_csr_count(const float* d_dense, int64_t M, int64_t K, int64_t ld, int32_t* d_row_ptr,
+                            int64_t* h_nnz, void* stream) {
+  B200_REQUIRE(M >= 0 && K >= 0 && M < 0x7fffffffLL && K < 0x7fffffffLL, "dimension out of range");
+  B200_REQUIRE(ld >= K, "leading dimension smaller than K");
+  B200_REQUIRE(d_row_ptr != nullptr, "null row_ptr");
+  B200_REQUIRE(M == 0 || K == 0 || d_dense != nullptr, "null dense");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_dense_count(d_dense, (int)M, (int)K, ld, d_row_ptr, s);
+  if (rc) return rc;
+  if (h_nnz) {
+    int n = 0;
+    B200_CUDA_OK(cudaMemcpyAsync(&n, d_row_ptr + M, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    *h_nnz = n;
+  }
+  return B200_OK;
+}
+
+int b200_dense_to_csr_fill(const float* d_dense, int64_t M, int64_t K, int64_t ld,
+                           const int32_t* d_row_ptr, int32_t* d_col_ind, float* d_val, void* stream) {
+  B200_REQUIRE(M >= 0 && K >= 0 && M < 0x7fffffffLL && K < 0x7fffffffLL, "dimension out of range");
+  B200_REQUIRE(ld >= K, "leading dimension smaller than K");
+  if (M == 0 || K == 0) return B200_OK;
+  B200_REQUIRE(d_dense && d_row_ptr, "null dense / row_ptr");
+  return launch_dense_fill(d_dense, (int)M, (int)K, ld, d_row_ptr, d_col_ind, d_val, (cudaStream_t)stream);
+}
+
+int b200_dense_to_csr_alloc(const float* d_dense, int64_t M, int64_t K, int64_t ld, float** d_val,
+                            int32_t** d_col_ind, int32_t** d_row_ptr, int64_t* nnz, void* stream) {
+  B200_REQUIRE(d_val && d_col_ind && d_row_ptr && nnz, "null output pointer");
+  B200_REQUIRE(M >= 0 && K >= 0 && M < 0x7fffffffLL && K < 0x7fffffffLL, "dimension out of range");
+  *d_val = nullptr; *d_col_ind = nullptr; *d_row_ptr = nullptr; *nnz = 0;
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(d_row_ptr), ((size_t)M + 1) * sizeof(int)));
+  int rc = b200_dense_to_csr_count(d_dense, M, K, ld, *d_row_ptr, nnz, stream);
+  if (rc) return rc;
+  const size_t n = std::max<size_t>((size_t)*nnz, 1);
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(d_col_ind), n * sizeof(int)));
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(d_val), n * sizeof(float)));
+  rc = b200_dense_to_csr_fill(d_dense, M, K, ld, *d_row_ptr, *d_col_ind, *d_val, stream);
+  if (rc) return rc;
+  B200_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return B200_OK;
+}
+
+int b200_free_csr(float* d_val, int32_t* d_col_ind, int32_t* d_row_ptr) {
+  B200_CUDA_OK(cudaFree(d_val));
+  B200_CUDA_OK(cudaFree(d_col_ind));
+  B200_CUDA_OK(cudaFree(d_row_ptr));
+  return B200_OK;
+}
+
+// ---- plans ---------------------------------------------------------------------------
+int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val, int64_t M,
+                     int64_t K, int64_t nnz, b200_plan** out_plan, void* stream) {
+  B200_REQUIRE(out_plan != nullptr, "null out_plan");
+  *out_plan = nullptr;
+  int rc = check_device();
+  if (rc) return rc;
+  rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(d_row_ptr != nullptr, "null row_ptr");
+  B200_REQUIRE(nnz == 0 || (d_col_ind && d_val), "null col/val");
+  b200_plan* p = new (std::nothrow) b200_plan();
+  if (!p) { set_error("out of host memory"); return B200_ERR_ALLOC; }
+  p->row_ptr = d_row_ptr; p->col = d_col_ind; p->val = d_val;
+  p->M = (int)M; p->K = (int)K; p->nnz = (int)nnz;
+  cudaStream_t s = (cudaStream_t)stream;
+  int* d_stats = nullptr;
+  int h_stats[2] = {0, 0};
+  if (cudaMalloc(&d_stats, 2 * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError(); delete p; set_error("cudaMalloc failed"); return B200_ERR_ALLOC;
+  }
+  rc = launch_row_stats(d_row_ptr, (int)M, d_stats, s);
+  if (rc == B200_OK) {
+    cudaError_t e = cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("row stats copy failed: %s", cudaGetErrorString(e)); rc = B200_ERR_CUDA; }
+  }
+  cudaFree(d_stats);
+  if (rc) { delete p; return rc; }
+  p->max_row = h_stats[0];
+  p->empty_rows = h_stats[1];
+  *out_plan = p;
+  return B200_OK;
+}
+
+int b200_plan_destroy(b200_plan* p) {
+  if (!p) return B200_OK;
+  cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
+  cudaGetLastError();
+  delete p;
+  return B200_OK;
+}
+
+int b200_plan_values_updated(b200_plan* p) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  p->t_val_stale = true;
+  return B200_OK;
+}
+
+int b200_plan_stats(const b200_plan* p, int64_t* max_row_nnz, int64_t* empty_rows) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  if (max_row_nnz) *max_row_nnz = p->max_row;
+  if (empty_rows) *empty_rows = p->empty_rows;
+  return B200_OK;
+}
+
+int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
+                      void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  int rc = plan_ensure_ws(p, fwd_workspace_bytes(std::max(p->M, p->K), p->nnz, N));
+  if (rc) return rc;
+  return b200_spmm_csr_forward(p->row_ptr, p->col, p->val, p->M, p->K, p->nnz, d_B, ldb, N, d_C, ldc,
+                               p->ws, p->ws_bytes, stream);
+}
+
+int b200_plan_backward_B(b200_plan* p, const float* d_G, int64_t ldg, int64_t N, float* d_dB,
+                         int64_t lddb, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  int rc = plan_ensure_transpose(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = plan_ensure_ws(p, fwd_workspace_bytes(std::max(p->M, p->K), p->nnz, N));
+  if (rc) return rc;
+  return b200_spmm_csr_forward(p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->nnz, d_G, ldg, N, d_dB,
+                               lddb, p->ws, p->ws_bytes, stream);
+}
+
+int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,
+                         int64_t N, float* d_dval, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  return b200_sddmm_csr(p->row_ptr, p->col, p->M, p->K, p->nnz, d_G, ldg, d_B, ldb, N, d_dval, stream);
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------
+
+int b200_spmm_csr_forward_host(const int32_t* h_row_ptr, const int32_t* h_col_ind, const float* h_val,
+                               int64_t M, int64_t K, int64_t nnz, const float* h_B, int64_t N,
+                               float* h_C) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(N >= 0, "negative N");
+  if (M == 0 || N == 0) return B200_OK;
+  B200_REQUIRE(h_row_ptr && h_C && (nnz == 0 || (h_col_ind && h_val && h_B)), "null host pointer");
+  cudaStream_t s = nullptr;
+  DevBuf rp, ci, va, b, c;
+  if ((rc = rp.alloc((M + 1) * 4)) || (rc = ci.alloc(nnz * 4)) || (rc = va.alloc(nnz * 4)) ||
+      (rc = b.alloc((size_t)K * N * 4)) || (rc = c.alloc((size_t)M * N * 4)))
+    return rc;
+  H2D(rp.p, h_row_ptr, (size_t)(M + 1) * 4, s);
+  H2D(ci.p, h_col_ind, (size_t)nnz * 4, s);
+  H2D(va.p, h_val, (size_t)nnz * 4, s);
+  if (nnz > 0) H2D(b.p, h_B, (size_t)K * N * 4, s);
+  rc = b200_spmm_csr_forward(rp.as<int>(), ci.as<int>(), va.as<float>(), M, K, nnz, b.as<float>(), N, N,
+                             c.as<float>(), N, nullptr, 0, s);
+  if (rc) return rc;
+  D2H(h_C, c.p, (size_t)M * N * 4, s);
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_sddmm_csr_host(const int32_t* h_row_ptr, const int32_t* h_col_ind, int64_t M, int64_t K,
+                        int64_t nnz, const float* h_G, const float* h_B, int64_t N, float* h_out_val) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(N >= 0, "negative N");
+  if (nnz == 0) return B200_OK;
+  B200_REQUIRE(h_row_ptr && h_col_ind && h_out_val && (N == 0 || (h_G && h_B)), "null host pointer");
+  cudaStream_t s = nullptr;
+  DevBuf rp, ci, g, b, o;
+  if ((rc = rp.alloc((M + 1) * 4)) || (rc = ci.alloc(nnz * 4)) || (rc = g.alloc((size_t)M * N * 4)) ||
+      (rc = b.alloc((size_t)K * N * 4)) || (rc = o.alloc(nnz * 4)))
+    return rc;
+  H2D(rp.p, h_row_ptr, (size_t)(M + 1) * 4, s);
+  H2D(ci.p, h_col_ind, (size_t)nnz * 4, s);
+  H2D(g.p, h_G, (size_t)M * N * 4, s);
+  H2D(b.p, h_B, (size_t)K * N * 4, s);
+  rc = b200_sddmm_csr(rp.as<int>(), ci.as<int>(), M, K, nnz, g.as<float>(), N, b.as<float>(), N, N,
+                      o.as<float>(), s);
+  if (rc) return rc;
+  D2H(h_out_val, o.p, (size_t)nnz * 4, s);
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_csr_transpose_host(const int32_t* h_row_ptr, const int32_t* h_col_ind, const float* h_val,
+                            int64_t M, int64_t K, int64_t nnz, int32_t* h_t_row_ptr,
+                            int32_t* h_t_col_ind, float* h_t_val) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(h_row_ptr && h_t_row_ptr, "null host pointer");
+  B200_REQUIRE(nnz == 0 || (h_col_ind && h_val && h_t_col_ind && h_t_val), "null host pointer");
+  cudaStream_t s = nullptr;
+  DevBuf rp, ci, va, trp, tci, tva;
+  if ((rc = rp.alloc((M + 1) * 4)) || (rc = ci.alloc(nnz * 4)) || (rc = va.alloc(nnz * 4)) ||
+      (rc = trp.alloc((K + 1) * 4)) || (rc = tci.alloc(nnz * 4)) || (rc = tva.alloc(nnz * 4)))
+    return rc;
+  H2D(rp.p, h_row_ptr, (size_t)(M + 1) * 4, s);
+  H2D(ci.p, h_col_ind, (size_t)nnz * 4, s);
+  H2D(va.p, h_val, (size_t)nnz * 4, s);
+  rc = b200_csr_transpose(rp.as<int>(), ci.as<int>(), va.as<float>(), M, K, nnz, trp.as<int>(),
+                          tci.as<int>(), tva.as<float>(), nullptr, s);
+  if (rc) return rc;
+  D2H(h_t_row_ptr, trp.p, (size_t)(K + 1) * 4, s);
+  D2H(h_t_col_ind, tci.p, (size_t)nnz * 4, s);
+  D2H(h_t_val, tva.p, (size_t)nnz * 4, s);
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_spmm_csr_backward_B_host(const int32_t* h_row_ptr, const int32_t* h_col_ind, const float* h_val,
+                                  int64_t M, int64_t K, int64_t nnz, const float* h_G, int64_t N,
+                                  float* h_dB) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = check_csr_dims(M, K, nnz);
+  if (rc) return rc;
+  B200_REQUIRE(N >= 0, "negative N");
+  if (K == 0 || N == 0) return B200_OK;
+  B200_REQUIRE(h_row_ptr && h_dB && (nnz == 0 || (h_col_ind && h_val && h_G)), "null host pointer");
+  cudaStream_t s = nullptr;
+  DevBuf rp, ci, va, g, db;
+  if ((rc = rp.alloc((M + 1) * 4)) || (rc = ci.alloc(nnz * 4)) || (rc = va.alloc(nnz * 4)) ||
+      (rc = g.alloc((size_t)M * N * 4)) || (rc = db.alloc((size_t)K * N * 4)))
+    return rc;
+  H2D(rp.p, h_row_ptr, (size_t)(M + 1) * 4, s);
+  H2D(ci.p, h_col_ind, (size_t)nnz * 4, s);
+  H2D(va.p, h_val, (size_t)nnz * 4, s);
+  if (nnz > 0) H2D(g.p, h_G, (size_t)M * N * 4, s);
+  b200_plan* plan = nullptr;
+  rc = b200_plan_create(rp.as<int>(), ci.as<int>(), va.as<float>(), M, K, nnz, &plan, s);
+  if (rc) return rc;
+  rc = b200_plan_backward_B(plan, g.as<float>(), N, N, db.as<float>(), N, s);
+  if (rc == B200_OK) {
+    cudaError_t e = cudaMemcpyAsync(h_dB, db.p, (size_t)K * N * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = B200_ERR_CUDA; }
+  }
+  b200_plan_destroy(plan);
+  return rc;
+}
+
+int b200_dense_to_csr_host(const float* h_dense, int64_t M, int64_t K, int32_t* h_row_ptr,
+                           int32_t* h_col_ind, float* h_val, int64_t capacity, int64_t* nnz) {
+  int rc = check_device();
+  if (rc) return rc;
+  B200_REQUIRE(M >= 0 && K >= 0 && M < 0x7fffffffLL && K < 0x7fffffffLL, "dimension out of range");
+  B200_REQUIRE(nnz != nullptr && h_row_ptr != nullptr, "null nnz / row_ptr");
+  B200_REQUIRE(M == 0 || K == 0 || h_dense != nullptr, "null dense");
+  cudaStream_t s = nullptr;
+  DevBuf d, rp, ci, va;
+  if ((rc = d.alloc((size_t)M * K * 4)) || (rc = rp.alloc((M + 1) * 4))) return rc;
+  H2D(d.p, h_dense, (size_t)M * K * 4, s);
+  rc = b200_dense_to_csr_count(d.as<float>(), M, K, K, rp.as<int>(), nnz, s);
+  if (rc) return rc;
+  D2H(h_row_ptr, rp.p, (size_t)(M + 1) * 4, s);
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  if (*nnz > capacity) {
+    set_error("capacity %lld too small for %lld non-zeros", (long long)capacity, (long long)*nnz);
+    return B200_ERR_INVALID;
+  }
+  if (*nnz == 0) return B200_OK;
+  B200_REQUIRE(h_col_ind && h_val, "null col/val");
+  if ((rc = ci.alloc(*nnz * 4)) || (rc = va.alloc(*nnz * 4))) return rc;
+  rc = b200_dense_to_csr_fill(d.as<float>(), M, K, K, rp.as<int>(), ci.as<int>(), va.as<float>(), s);
+  if (rc) return rc;
+  D2H(h_col_ind, ci.p, (size_t)*nnz * 4, s);
+  D2H(h_val, va.p, (size_t)*nnz * 4, s);
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+// ---- host-side partition helpers ---------------------------------------------------------
+int b200_merge_path_boundary(const int32_t* h_row_ptr, int64_t M, int64_t nnz, int64_t d,
+                             int64_t heavy_threshold, int64_t* row, int64_t* nz) {
+  B200_REQUIRE(h_row_ptr && row && nz, "null pointer");
+  B200_REQUIRE(M >= 0 && nnz >= 0 && M < 0x7fffffffLL && nnz < 0x7fffffffLL, "dimension out of range");
+  B200_REQUIRE(heavy_threshold >= 0 && heavy_threshold < 0x7fffffffLL, "heavy threshold out of range");
+  Boundary b = merge_path_boundary(h_row_ptr, (int)M, (int)nnz, d, (int)heavy_threshold);
+  *row = b.row;
+  *nz = b.nz;
+  return B200_OK;
+}
+
+int b200_shard_rows(const int32_t* h_row_ptr, int64_t M, int parts, double nnz_weight,
+                    double row_weight, int64_t* bounds) {
+  B200_REQUIRE(h_row_ptr && bounds, "null pointer");
+  B200_REQUIRE(M >= 0 && parts >= 1, "bad M / parts");
+  B200_REQUIRE(nnz_weight >= 0 && row_weight >= 0 && (nnz_weight + row_weight) > 0, "bad weights");
+  // cost(r) = nnz_weight * row_ptr[r] + row_weight * r is non-decreasing; shard g starts at the
+  // first row whose prefix cost reaches g/parts of the total.
+  const double total = nnz_weight * (double)h_row_ptr[M] + row_weight * (double)M;
+  bounds[0] = 0;
+  for (int g = 1; g < parts; ++g) {
+    const double target = total * (double)g / (double)parts;
+    int64_t lo = 0, hi = M;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      double c = nnz_weight * (double)h_row_ptr[mid] + row_weight * (double)mid;
+      if (c >= target) hi = mid; else lo = mid + 1;
+    }
+    bounds[g] = std::max(lo, bounds[g - 1]);
+  }
+  bounds[parts] = M;
+  return B200_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

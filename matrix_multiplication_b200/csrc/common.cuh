@@ -1,0 +1,206 @@
+// common.cuh — shared helpers of the sm_100a SpMM engine: status handling, PTX
+// wrappers (mbarrier + TMA bulk copy, cache-hinted loads/stores) and the
+// merge-path task boundary that every kernel and the host planner agree on.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/spmm_b200.h"
+
+namespace b200 {
+
+// ---- status ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define B200_CUDA_OK(expr)                                                            \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                        __FILE__, __LINE__);                                          \
+      return B200_ERR_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+
+#define B200_REQUIRE(cond, msg)                                                       \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      ::b200::set_error("invalid argument: %s (%s)", msg, #cond);                     \
+      return B200_ERR_INVALID;                                                        \
+    }                                                                                 \
+  } while (0)
+
+#define B200_LAUNCH_OK(name)                                                          \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ::b200::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \
+      return B200_ERR_CUDA;                                                           \
+    }                                                                                 \
+    ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+  } while (0)
+
+// process-wide options (capi.cu)
+struct Options {
+  int stage_mode = 1;      // 1: TMA bulk staging of col/val, 0: direct global loads
+  int items_per_task = 0;  // 0 = auto
+  int batch = 0;           // reserved
+};
+Options& options();
+
+int device_sm_count();
+
+// ---- merge-path boundary ----------------------------------------------------------
+// Items are consumed in the order: non-zeros of row 0, row-end 0, non-zeros of
+// row 1, row-end 1, ...  Item index of row-end r is row_ptr[r+1] + r.
+// boundary(d) = (i, j): rows < i are complete, j non-zeros are consumed.
+// If the boundary falls inside row i and that row is "light" (length <= heavy),
+// it is snapped down to the row start so light rows are never split.
+struct Boundary {
+  int row;
+  int nz;
+};
+
+__host__ __device__ __forceinline__ Boundary merge_path_boundary(
+    const int* __restrict__ row_ptr, int M, int nnz, long long d, int heavy) {
+  long long total = (long long)M + (long long)nnz;
+  if (d >= total) return Boundary{M, nnz};
+  if (d <= 0) return Boundary{0, 0};
+  // smallest i in [0, M) with row_ptr[i+1] + i >= d   (exists because d < total)
+  int lo = 0, hi = M - 1;
+  while (lo < hi) {
+    int mid = (int)(((long long)lo + hi) >> 1);
+#if defined(__CUDA_ARCH__)
+    long long g = (long long)__ldg(row_ptr + mid + 1) + mid;
+#else
+    long long g = (long long)row_ptr[mid + 1] + mid;
+#endif
+    if (g >= d) hi = mid; else lo = mid + 1;
+  }
+  int i = lo;
+  int j = (int)(d - i);
+#if defined(__CUDA_ARCH__)
+  int rs = __ldg(row_ptr + i), re = __ldg(row_ptr + i + 1);
+#else
+  int rs = row_ptr[i], re = row_ptr[i + 1];
+#endif
+  if (j > rs && (re - rs) <= heavy) j = rs;
+  return Boundary{i, j};
+}
+
+#if defined(__CUDACC__)
+// ---- PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// read-only 128/64/32-bit loads of B (gathered rows; keep in L1/L2)
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store_stream(float* p) const {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  }
+  __device__ __forceinline__ void store_stream(float* p) const {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+};
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, v[0]); }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+#endif  // __CUDACC__
+
+// ---- internal launchers (one per .cu) -------------------------------------------------
+struct FwdParams {
+  const int* row_ptr;
+  const int* col;
+  const float* val;
+  int M;
+  int nnz;
+  const float* B;
+  long long ldb;
+  int N;
+  float* C;
+  long long ldc;
+  float* pieces;   // workspace: [2 * n_tasks][N] partial rows of split heavy rows
+  int* split_flag; // workspace: set to 1 when any piece was written
+  int stage;       // 1 / 0 force TMA staging on / off, -1 = process option
+};
+size_t fwd_workspace_bytes(long long M, long long nnz, long long N);
+int launch_spmm_forward(const FwdParams& p, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
+                 const float* B, long long ldb, int N, float* out, cudaStream_t s);
+int launch_transpose(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz,
+                     int* t_row_ptr, int* t_col, float* t_val, int* t_perm, cudaStream_t s);
+int launch_gather(const float* src, const int* perm, long long n, float* dst, cudaStream_t s);
+int launch_dense_count(const float* dense, int M, int K, long long ld, int* row_ptr, cudaStream_t s);
+int launch_dense_fill(const float* dense, int M, int K, long long ld, const int* row_ptr, int* col,
+                      float* val, cudaStream_t s);
+int launch_row_stats(const int* row_ptr, int M, int* d_out2 /* max_len, empty */, cudaStream_t s);
+
+// per-device cached scratch (grown on demand; stream-ordered use only)
+int get_scratch(size_t bytes, void** ptr);
+
+}  // namespace b200

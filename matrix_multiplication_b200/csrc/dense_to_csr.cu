@@ -1,0 +1,187 @@
+// dense_to_csr.cu — dense row-major fp32 [M,K] -> CSR (row_ptr int32, col_ind int32, val fp32).
+//
+// Replaces dense_to_csr (reference src/baseline_mm.cu:218-264, cuSPARSE
+// DenseToSparse) and the per-call `a.to_sparse_csr()` of matmuls.py:215,228.
+// Bit-exact contract: keep x != 0 (so NaN is kept and -0.0 is dropped), row-major
+// order, values copied bit for bit (the test is done on the bit pattern so that
+// flush-to-zero settings cannot turn a denormal into a dropped element).
+//
+//   count: one warp per row, 128-bit loads, ballot/popc -> per-row counts
+//   scan : one CTA, shuffle-based block scan with a running carry -> row_ptr
+//   fill : one warp per row, ballot + popc(mask below lane) gives every kept
+//          element its output slot; writes are contiguous per row.
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ bool keep(float x) { return (__float_as_uint(x) & 0x7fffffffu) != 0u; }
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+count_kernel(const float* __restrict__ dense, int M, int K, long long ld, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps_per_grid) {
+    const float* r = dense + (long long)row * ld;
+    int cnt = 0;
+    if (VEC4) {
+      const int K4 = K >> 2;
+      const float4* r4 = reinterpret_cast<const float4*>(r);
+      for (int c = lane; c < K4; c += 32) {
+        float4 x = __ldcs(r4 + c);
+        cnt += keep(x.x) + keep(x.y) + keep(x.z) + keep(x.w);
+      }
+      for (int c = (K4 << 2) + lane; c < K; c += 32) cnt += keep(__ldcs(r + c));
+    } else {
+      for (int c = lane; c < K; c += 32) cnt += keep(__ldcs(r + c));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    if (lane == 0) counts[row] = cnt;
+  }
+}
+
+// In-place exclusive scan of counts[0..M) into row_ptr[0..M]; row_ptr[M] = total.
+__global__ void __launch_bounds__(1024) scan_kernel(int* __restrict__ data, int M) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  constexpr int PER = 4;
+  for (int base = 0; base < M; base += 1024 * PER) {
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int idx = base + tid * PER + i;
+      v[i] = (idx < M) ? data[idx] : 0;
+      sum += v[i];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(FULL, wi, o);
+        if (lane >= o) wi += n;
+      }
+      warp_sums[lane] = wi - w;  // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int excl = carry + warp_sums[warp] + (incl - sum);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int idx = base + tid * PER + i;
+      if (idx < M) data[idx] = excl;
+      excl += v[i];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = excl;  // total including this chunk
+    __syncthreads();
+  }
+  if (tid == 0) data[M] = carry_s;
+}
+
+__global__ void __launch_bounds__(256)
+fill_kernel(const float* __restrict__ dense, int M, int K, long long ld,
+            const int* __restrict__ row_ptr, int* __restrict__ col, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps_per_grid) {
+    const float* r = dense + (long long)row * ld;
+    int base = __ldg(row_ptr + row);
+    const int end = __ldg(row_ptr + row + 1);
+    if (base == end) continue;  // nothing to write for this row
+    for (int c0 = 0; c0 < K; c0 += 128) {
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * 32 + lane;
+        x[u] = (c < K) ? __ldcs(r + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool k = keep(x[u]);
+        const unsigned ball = __ballot_sync(FULL, k);
+        if (k) {
+          const int pos = base + __popc(ball & lt);
+          col[pos] = c0 + u * 32 + lane;
+          val[pos] = x[u];
+        }
+        base += __popc(ball);
+      }
+    }
+  }
+}
+
+__global__ void row_stats_kernel(const int* __restrict__ row_ptr, int M, int* __restrict__ out2) {
+  int mx = 0, empty = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
+    int len = __ldg(row_ptr + r + 1) - __ldg(row_ptr + r);
+    mx = max(mx, len);
+    empty += (len == 0);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+    empty += __shfl_xor_sync(FULL, empty, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out2, mx);
+    atomicAdd(out2 + 1, empty);
+  }
+}
+
+inline int warp_grid(int M) {
+  long long ctas = ((long long)M + 7) / 8;  // 8 warps per CTA, one row per warp
+  long long cap = 148LL * 8;
+  return (int)(ctas < 1 ? 1 : (ctas > cap ? cap : ctas));
+}
+
+}  // namespace
+
+int launch_dense_count(const float* dense, int M, int K, long long ld, int* row_ptr, cudaStream_t s) {
+  if (M == 0) {
+    B200_CUDA_OK(cudaMemsetAsync(row_ptr, 0, sizeof(int), s));
+    return B200_OK;
+  }
+  const bool v4 = (reinterpret_cast<uintptr_t>(dense) % 16 == 0) && (ld % 4 == 0);
+  if (v4) count_kernel<true><<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr);
+  else count_kernel<false><<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr);
+  B200_LAUNCH_OK("dense_count_kernel");
+  scan_kernel<<<1, 1024, 0, s>>>(row_ptr, M);
+  B200_LAUNCH_OK("dense_scan_kernel");
+  return B200_OK;
+}
+
+int launch_dense_fill(const float* dense, int M, int K, long long ld, const int* row_ptr, int* col,
+                      float* val, cudaStream_t s) {
+  if (M == 0 || K == 0) return B200_OK;
+  fill_kernel<<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr, col, val);
+  B200_LAUNCH_OK("dense_fill_kernel");
+  return B200_OK;
+}
+
+int launch_row_stats(const int* row_ptr, int M, int* d_out2, cudaStream_t s) {
+  B200_CUDA_OK(cudaMemsetAsync(d_out2, 0, 2 * sizeof(int), s));
+  if (M == 0) return B200_OK;
+  int blocks = (int)std::min<long long>(((long long)M + 255) / 256, 148 * 8);
+  row_stats_kernel<<<blocks, 256, 0, s>>>(row_ptr, M, d_out2);
+  B200_LAUNCH_OK("row_stats_kernel");
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,109 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports what the header declares,
+the merge-path cut and the row sharding behave, and the forward kernel's decomposition (simulated in
+numpy on the library's own boundary function) reproduces the oracle.  No compute calls on a GPU."""
+import numpy as np
+import pytest
+
+from matrix_multiplication_b200 import capi
+from oracle import oracle
+from conftest import random_csr
+from taskwalk_sim import simulate
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    declared = capi.declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/spmm_b200.h but not exported"
+        assert name in capi.SIGNATURES, f"{name} has no ctypes signature in _capi.py"
+    assert L.b200_abi_version() == 1
+    assert b"sm_100a" in L.b200_build_info()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rp = np.array([0, 1], dtype=np.int32)
+    with pytest.raises(capi.B200Error) as e:
+        capi.spmm_host(rp, np.zeros(1, np.int32), np.ones(1, np.float32), (1, 1), np.ones((1, 4), np.float32))
+    assert e.value.status in (capi.ERR_NO_DEVICE, capi.ERR_CUDA)
+
+
+def test_argument_validation():
+    L = capi.lib()
+    assert L.b200_spmm_csr_forward(None, None, None, -1, 1, 0, None, 1, 1, None, 1, None, 0, None) == capi.ERR_INVALID
+    assert b"negative" in L.b200_last_error()
+    assert L.b200_spmm_csr_forward(None, None, None, 4, 4, 0, None, 2, 8, None, 8, None, 0, None) == capi.ERR_INVALID
+    assert L.b200_set_option(b"no_such_option", 1) == capi.ERR_INVALID
+    capi.set_option("items_per_task", 64)
+    assert capi.get_option("items_per_task") == 64
+    capi.set_option("items_per_task", 0)
+    assert L.b200_spmm_workspace_bytes(1000, 5000, 128) >= 256 + 2 * ((6000 + 127) // 128) * 128 * 4
+
+
+def test_merge_path_boundary_properties():
+    rng = np.random.default_rng(0)
+    for M, K, dens, heavy_rows in [(50, 40, 0.1, ()), (200, 300, 0.02, (7, 150)), (30, 2000, 0.001, (3,)),
+                                   (1, 500, 1.0, (0,)), (64, 8, 0.0, ())]:
+        rp, ci, va, _ = random_csr(rng, M, K, dens, heavy_rows=heavy_rows)
+        nnz = int(rp[-1])
+        for W in (1, 7, 32, 256):
+            n_tasks = max(1, -(-(M + nnz) // W))
+            prev = (0, 0)
+            assert capi.merge_path_boundary(rp, 0, W) == (0, 0)
+            for t in range(1, n_tasks + 1):
+                i, j = capi.merge_path_boundary(rp, t * W, W)
+                assert prev[0] <= i <= M and prev[1] <= j <= nnz
+                if i < M:
+                    assert rp[i] <= j <= rp[i + 1]
+                    if j > rp[i]:                       # split rows are heavy ones only
+                        assert rp[i + 1] - rp[i] > W
+                        assert i + j == t * W           # and split exactly on the diagonal
+                assert (j - prev[1]) <= 2 * W           # task size bounded by W + heavy
+                prev = (i, j)
+            assert prev == (M, nnz)
+
+
+@pytest.mark.parametrize("W", [4, 32, 128])
+def test_taskwalk_simulation_matches_oracle(W):
+    rng = np.random.default_rng(W)
+    M, K, N = 120, 700, 5
+    rp, ci, va, dense = random_csr(rng, M, K, 0.01, heavy_rows=(0, 17, 18, 119), empty_rows=(1, 2, 3, 60, 118))
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    C, written, n_tasks, n_pieces = simulate(rp, ci, va, (M, K), B, W)
+    assert np.all(written == 1), "every row of C must be written exactly once"
+    ref = oracle.spmm_f64(rp, ci, va, (M, K), B)
+    assert oracle.rel_err(C, ref) <= 1e-12
+    assert n_pieces > 0
+
+
+def test_taskwalk_heavy_row_ending_on_a_diagonal():
+    # row lengths chosen so that a heavy row's row-end item lands exactly on a task boundary
+    W = 8
+    lens = [3, 20, 0, 0, 13, 1]           # items: 3+1, 20+1, 1, 1, 13+1, 1+1
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nnz = int(rp[-1])
+    rng = np.random.default_rng(1)
+    ci = rng.integers(0, 9, nnz).astype(np.int32)
+    va = rng.standard_normal(nnz).astype(np.float32)
+    B = rng.standard_normal((9, 3)).astype(np.float32)
+    for W in range(1, 30):
+        C, written, _, _ = simulate(rp, ci, va, (len(lens), 9), B, W)
+        assert np.all(written == 1), W
+        assert oracle.rel_err(C, oracle.spmm_f64(rp, ci, va, (len(lens), 9), B)) <= 1e-12, W
+
+
+def test_shard_rows_balances_nnz():
+    rng = np.random.default_rng(5)
+    lens = np.minimum((rng.pareto(1.2, 20000) * 3).astype(np.int64), 5000)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    for parts in (1, 2, 4, 8):
+        b = capi.shard_rows(rp, parts, 1.0, 0.0)
+        assert b[0] == 0 and b[-1] == len(lens) and np.all(np.diff(b) >= 0)
+        per = np.diff(rp[b].astype(np.int64))
+        assert per.sum() == rp[-1]
+        assert per.max() <= rp[-1] / parts + lens.max()
+    b = capi.shard_rows(rp, 4, 0.0, 1.0)      # rows only
+    assert np.all(np.abs(np.diff(b) - len(lens) / 4) <= 1)
