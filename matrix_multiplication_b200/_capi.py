@@ -218,3 +218,75 @@ def smoke() -> int:
     n = C.c_int(0)
     check(lib().b200_smoke_kernel(None, C.byref(n)))
     return n.value
+
+
+# ---- device-pointer calls (anything with .data_ptr(): torch CUDA tensors) -------------------------
+def _dp(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def spmm_device(crow, col, val, shape, B, Cout, ldb=None, ldc=None, workspace=None, stream=0, flags=0):
+    """b200_spmm_csr_forward_flags on device buffers; Cout is written in place."""
+    M, K = shape
+    N = B.shape[1]
+    ws_p, ws_n = (None, 0) if workspace is None else (_dp(workspace), workspace.numel() * workspace.element_size())
+    check(lib().b200_spmm_csr_forward_flags(_dp(crow), _dp(col), _dp(val), M, K, val.numel(), _dp(B),
+                                            N if ldb is None else ldb, N, _dp(Cout),
+                                            N if ldc is None else ldc, ws_p, ws_n,
+                                            C.c_void_p(stream), flags))
+    return Cout
+
+
+def sddmm_device(crow, col, shape, G, B, out, stream=0):
+    M, K = shape
+    N = G.shape[1]
+    check(lib().b200_sddmm_csr(_dp(crow), _dp(col), M, K, col.numel(), _dp(G), N, _dp(B), N, N, _dp(out),
+                               C.c_void_p(stream)))
+    return out
+
+
+class Plan:
+    """inspect / execute / clean on device buffers (b200_plan_*); borrows crow/col/val."""
+
+    def __init__(self, crow, col, val, shape, stream=0):
+        self._keep = (crow, col, val)
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = val.numel()
+        h = C.c_void_p()
+        check(lib().b200_plan_create(_dp(crow), _dp(col), _dp(val), self.shape[0], self.shape[1], self.nnz,
+                                     C.byref(h), C.c_void_p(stream)))
+        self._h = h
+
+    def forward(self, B, Cout, stream=0):
+        N = B.shape[1]
+        check(lib().b200_plan_forward(self._h, _dp(B), N, N, _dp(Cout), N, C.c_void_p(stream)))
+        return Cout
+
+    def backward_B(self, G, dB, stream=0):
+        N = G.shape[1]
+        check(lib().b200_plan_backward_B(self._h, _dp(G), N, N, _dp(dB), N, C.c_void_p(stream)))
+        return dB
+
+    def backward_A(self, G, B, dval, stream=0):
+        N = G.shape[1]
+        check(lib().b200_plan_backward_A(self._h, _dp(G), N, _dp(B), N, N, _dp(dval), C.c_void_p(stream)))
+        return dval
+
+    def values_updated(self):
+        check(lib().b200_plan_values_updated(self._h))
+
+    def stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().b200_plan_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if self._h is not None:
+            lib().b200_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

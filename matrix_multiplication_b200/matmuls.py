@@ -167,13 +167,14 @@ class cublasTransabMM(InplaceFunction):
 class CsrMatrix:
     '''Device CSR (int32 indices, fp32 values) plus the lazily built, cached transpose.'''
 
-    __slots__ = ('crow', 'col', 'val', 'shape', '_t', '_key')
+    __slots__ = ('crow', 'col', 'val', 'shape', '_t', '_key', '_val_key')
 
     def __init__(self, crow, col, val, shape, key=None):
         self.crow, self.col, self.val = crow, col, val
         self.shape = (int(shape[0]), int(shape[1]))
         self._t = None
         self._key = key
+        self._val_key = None
 
     @property
     def nnz(self):
@@ -197,6 +198,13 @@ class CsrMatrix:
         if self._t is not None:
             t, perm = self._t
             t.val = custom_mm.gather(val, perm)
+
+    def refresh_values_if_changed(self, values):
+        '''Parameter-backed values (cusparseLinear): re-gather the transpose only after an update.'''
+        key = (values.data_ptr(), values._version)
+        if key != self._val_key:
+            self.refresh_values(values.detach())
+            self._val_key = key
 
     def to_torch(self, values=None):
         return torch.sparse_csr_tensor(self.crow, self.col, self.val if values is None else values,
