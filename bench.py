@@ -86,22 +86,64 @@ def flops(w) -> int:
 # clocks (nvidia-smi sampled during the timed region)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every few ms during the timed region (NVML; nvidia-smi fallback)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons = index, [], None, set()
+        self._stop, self._t, self.power = threading.Event(), None, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        self.h = h
+                        break
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for n, bit in self.BAD.items():
+                if r & bit:
+                    self.reasons.add(n)
+            try:
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+        else:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self.index)], capture_output=True, text=True, timeout=5).stdout
+            r = [x.strip() for x in out.strip().split(",")]
+            self.sm.append(float(r[0])); self.mx = float(r[1])
+            for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                self._sample()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -113,22 +155,13 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
+        out = {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+               "samples": len(self.sm)}
+        if self.power:
+            out["power_w_max"] = round(max(self.power), 1)
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -256,6 +289,9 @@ def run_ours(args):
     N, nnz = w["N"], len(w["val"])
     dev = torch.device("cuda", local)
     custom_mm.init_cusparse()
+    for o in args.opt:
+        name, value = o.split("=")
+        capi.set_option(name, int(value))
 
     # ---- shard A's rows (nnz-balanced cost; one shard when world == 1) -----------------------------
     bounds = sharding.shard_bounds(w["row_ptr"], world, N)
@@ -465,6 +501,7 @@ def main():
     ap.add_argument("--scale", type=int, default=None, help="R-MAT scale (c4) or matrix dimension (c5) override")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-comparators", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (b200_set_option)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture")
     args = ap.parse_args()

@@ -96,7 +96,34 @@ struct b200_plan {
   // owned scratch for forward / backward_B
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // cached merge-path boundaries of A (fwd) and A^T (bwd), valid for the FwdPick stored beside them
+  Boundary* bnd[2] = {nullptr, nullptr};
+  FwdPick pick[2];
+  bool bnd_valid[2] = {false, false};
+  int t_max_row = -1;
 };
+
+// Boundaries depend on (row_ptr, W, heavy) only: compute once per plan side, reuse for every N.
+static int plan_ensure_bounds(b200_plan* p, int side, const int* row_ptr, int M, int max_row, int64_t N,
+                              cudaStream_t s) {
+  FwdPick k = fwd_pick(M, p->nnz, N, true, true, max_row);
+  if (p->bnd_valid[side] && p->pick[side].W == k.W && p->pick[side].heavy == k.heavy &&
+      p->pick[side].n_tasks == k.n_tasks)
+    return B200_OK;
+  if (p->bnd[side]) {
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    B200_CUDA_OK(cudaFree(p->bnd[side]));
+    p->bnd[side] = nullptr;
+  }
+  p->bnd_valid[side] = false;
+  if (p->nnz == 0 || M == 0) return B200_OK;
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->bnd[side]), fwd_bounds_bytes(k.n_tasks)));
+  int rc = launch_partition(row_ptr, M, p->nnz, k, p->bnd[side], s);
+  if (rc != B200_OK) return rc;
+  p->pick[side] = k;
+  p->bnd_valid[side] = true;
+  return B200_OK;
+}
 
 static int plan_ensure_ws(b200_plan* p, size_t need) {
   if (p->ws_bytes >= need) return B200_OK;
@@ -223,7 +250,7 @@ int b200_spmm_csr_forward_flags(const int32_t* d_row_ptr, const int32_t* d_col_i
   p.M = (int)M; p.nnz = (int)nnz;
   p.B = d_B; p.ldb = ldb; p.N = (int)N; p.C = d_C; p.ldc = ldc;
   p.stage = (flags & B200_FLAG_NO_STAGE) ? 0 : -1;
-  return launch_spmm_forward(p, d_workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_spmm_forward(p, d_workspace, workspace_bytes, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int b200_sddmm_csr(const int32_t* d_row_ptr, const int32_t* d_col_ind, int64_t M, int64_t K, int64_t nnz,
@@ -348,6 +375,7 @@ int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const f
 int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
+  cudaFree(p->bnd[0]); cudaFree(p->bnd[1]);
   cudaGetLastError();
   delete p;
   return B200_OK;
@@ -366,26 +394,38 @@ int b200_plan_stats(const b200_plan* p, int64_t* max_row_nnz, int64_t* empty_row
   return B200_OK;
 }
 
+static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M,
+                     int K, int max_row, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
+                     cudaStream_t s) {
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  B200_REQUIRE(ldb >= N && ldc >= N, "leading dimension smaller than N");
+  if (M == 0 || N == 0) return B200_OK;
+  B200_REQUIRE(d_C != nullptr && (p->nnz == 0 || d_B != nullptr), "null B / C");
+  int rc = plan_ensure_bounds(p, side, row_ptr, M, max_row, N, s);
+  if (rc) return rc;
+  rc = plan_ensure_ws(p, fwd_workspace_bytes(std::max(p->M, p->K), p->nnz, N));
+  if (rc) return rc;
+  FwdParams q{};
+  q.row_ptr = row_ptr; q.col = col; q.val = val; q.M = M; q.nnz = p->nnz;
+  q.B = d_B; q.ldb = ldb; q.N = (int)N; q.C = d_C; q.ldc = ldc; q.stage = -1;
+  return launch_spmm_forward(q, p->ws, p->ws_bytes, p->bnd_valid[side] ? p->bnd[side] : nullptr,
+                             p->bnd_valid[side] ? &p->pick[side] : nullptr, s);
+}
+
 int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
                       void* stream) {
   B200_REQUIRE(p != nullptr, "null plan");
-  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
-  int rc = plan_ensure_ws(p, fwd_workspace_bytes(std::max(p->M, p->K), p->nnz, N));
-  if (rc) return rc;
-  return b200_spmm_csr_forward(p->row_ptr, p->col, p->val, p->M, p->K, p->nnz, d_B, ldb, N, d_C, ldc,
-                               p->ws, p->ws_bytes, stream);
+  return plan_spmm(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc,
+                   (cudaStream_t)stream);
 }
 
 int b200_plan_backward_B(b200_plan* p, const float* d_G, int64_t ldg, int64_t N, float* d_dB,
                          int64_t lddb, void* stream) {
   B200_REQUIRE(p != nullptr, "null plan");
-  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
   int rc = plan_ensure_transpose(p, (cudaStream_t)stream);
   if (rc) return rc;
-  rc = plan_ensure_ws(p, fwd_workspace_bytes(std::max(p->M, p->K), p->nnz, N));
-  if (rc) return rc;
-  return b200_spmm_csr_forward(p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->nnz, d_G, ldg, N, d_dB,
-                               lddb, p->ws, p->ws_bytes, stream);
+  return plan_spmm(p, 1, p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->t_max_row, d_G, ldg, N, d_dB, lddb,
+                   (cudaStream_t)stream);
 }
 
 int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,

@@ -8,15 +8,17 @@
 //    same.  Task boundaries are snapped to row starts for light rows (<= W nnz);
 //    heavy rows are split exactly and their partial sums go to a scratch "piece"
 //    buffer that a tiny fix-up kernel adds up in task order (deterministic, no
-//    atomics, C is written exactly once per row).
-//  * A task is executed by a virtual warp of LPR lanes laid along the dense
-//    dimension (LPR * VEC columns = one slab): one 128-bit load of a B row per
-//    lane per non-zero, accumulation in CSR order.
+//    atomics, C is written exactly once per row).  The boundaries are computed once
+//    by partition_kernel (cached by a plan; recomputed per call otherwise).
+//  * One warp executes one task.  Its 32 lanes are laid out as G groups of LPR
+//    lanes: the LPR lanes span one slab of LPR*VEC dense columns (one 128-bit load
+//    of a B row per lane), the G groups take consecutive non-zeros of the same
+//    row; at a row end the G partial sums are combined with a warp-shuffle
+//    reduction.  Control flow is warp-uniform: no divergence inside a task.
 //  * The CTA's contiguous col/val segment is staged into shared memory with two
-//    TMA 1-D bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP) — the index
-//    fetch is off the critical path of the B gather.  Lanes then read the
-//    segment 32-at-a-time and broadcast with shuffles, issuing `U` independent
-//    B-row gathers before the FMAs (memory-level parallelism).
+//    TMA 1-D bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP) so that the index
+//    fetch is off the critical path of the B gather; lanes read it back with
+//    broadcast LDS.  `U` independent B-row gathers are issued before their FMAs.
 #include "common.cuh"
 
 namespace b200 {
@@ -24,51 +26,45 @@ namespace b200 {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS = 8;  // warps (= tasks) per CTA
 
-template <int LPR>
-struct Cfg {
-  static constexpr int GROUPS = 32 / LPR;               // virtual warps per warp
-  static constexpr int WARPS = (LPR >= 16) ? 8 : 4;     // warps per CTA
-  static constexpr int TASKS = WARPS * GROUPS;          // tasks per CTA
-  static constexpr int U = (LPR < 8) ? LPR : 8;         // gathers in flight per batch
-};
-
-__host__ __device__ inline int smem_capacity(int tasks, int W, int heavy) {
-  return ((tasks * W + heavy + 8) + 3) & ~3;  // non-zeros a CTA may have to stage
+__host__ __device__ inline int smem_capacity(int W, int heavy) {
+  return ((WARPS * W + heavy + 8) + 3) & ~3;  // non-zeros a CTA may have to stage
 }
 
-template <int LPR, int VEC, bool STAGE>
-__global__ void __launch_bounds__(Cfg<LPR>::WARPS * 32)
-spmm_fwd_kernel(FwdParams p, int W, int heavy, int n_tasks) {
-  using C = Cfg<LPR>;
+__global__ void __launch_bounds__(256)
+partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int heavy, int n_tasks,
+                 Boundary* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= n_tasks) out[t] = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, heavy);
+}
+
+template <int VEC, int LPR, int U, bool STAGE>
+__global__ void __launch_bounds__(WARPS * 32)
+spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy, int n_tasks) {
+  constexpr int G = 32 / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [mbar 16B][Boundary (TASKS+1)][pad16][s_col CAP][s_val CAP]
+  // layout: [mbar 16B][Boundary (WARPS+1), padded to 80B][s_col CAP][s_val CAP]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   Boundary* bnd_s = reinterpret_cast<Boundary*>(smem_raw + 16);
-  constexpr int BND_BYTES = ((C::TASKS + 1) * (int)sizeof(Boundary) + 15) & ~15;
-  const int cap = smem_capacity(C::TASKS, W, heavy);
+  constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
   int* s_col = reinterpret_cast<int*>(smem_raw + 16 + BND_BYTES);
-  float* s_val = reinterpret_cast<float*>(s_col + cap);
+  float* s_val = reinterpret_cast<float*>(s_col + smem_capacity(W, heavy));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int grp = lane / LPR, gl = lane % LPR;
-  const long long task0 = (long long)blockIdx.x * C::TASKS;
+  const int task0 = blockIdx.x * WARPS;
 
-  if (tid <= C::TASKS) {
-    long long t = task0 + tid;
-    if (t > n_tasks) t = n_tasks;
-    bnd_s[tid] = merge_path_boundary(p.row_ptr, p.M, p.nnz, t * (long long)W, heavy);
-  }
+  if (tid <= WARPS) bnd_s[tid] = bnd[min(task0 + tid, n_tasks)];
   if (STAGE && tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
 
-  const int jb = bnd_s[0].nz, je = bnd_s[C::TASKS].nz;
-  const int a0 = jb & ~3;  // staged window starts 16-byte aligned
+  const int a0 = bnd_s[0].nz & ~3;  // staged window starts 16-byte aligned
   if (STAGE) {
+    const int je = bnd_s[WARPS].nz;
     const int n_bulk = (je - a0) & ~3;
     if (tid == 0 && n_bulk > 0) {
       mbar_expect_tx(bar, (uint32_t)n_bulk * 8u);
@@ -82,130 +78,144 @@ spmm_fwd_kernel(FwdParams p, int W, int heavy, int n_tasks) {
     __syncthreads();
     if (n_bulk > 0) mbar_wait(bar, 0);
   }
+  // the non-zero stream of this CTA, indexed by global position
+  const int* cs = STAGE ? (s_col - a0) : p.col;
+  const float* vs = STAGE ? (s_val - a0) : p.val;
 
-  // ---- this virtual warp's task -----------------------------------------------------
-  const int tl = warp * C::GROUPS + grp;
-  const long long t = task0 + tl;
-  const Boundary b0 = bnd_s[tl], b1 = bnd_s[tl + 1];
-  const int i0 = b0.row, j0 = b0.nz, i1 = b1.row, j1 = b1.nz;
+  // ---- this warp's task ---------------------------------------------------------------
+  const int t = task0 + warp;
+  const Boundary b0 = bnd_s[warp], b1 = bnd_s[warp + 1];
+  const int i1 = b1.row, j1 = b1.nz;
+  int row = b0.row, pos = b0.nz;
+  if (row >= p.M) return;  // padding task
 
-  const int col0 = blockIdx.y * (LPR * VEC) + gl * VEC;
+  const int g = lane / LPR, l = lane % LPR;
+  const int col0 = blockIdx.y * (LPR * VEC) + l * VEC;
   const bool active = col0 < p.N;
-  const float* Bc = p.B + col0;
+  const bool writer = active && g == 0;
+  // inactive lanes gather from column 0 (always valid, never stored) so loads need no predicate
+  const float* Bc = p.B + (active ? col0 : 0);
 
-  int row = i0;
-  bool head = (i0 < p.M) && (j0 > __ldg(p.row_ptr + i0));  // first row continues a split row
-  int row_end = (row < p.M) ? __ldg(p.row_ptr + row + 1) : 0x7fffffff;
+  bool head = pos > __ldg(p.row_ptr + row);  // the first row continues a split heavy row
+
   float acc[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
-  auto flush = [&](int r) {
-    if (active) {
+  // acc += sum over non-zeros [q0, q1) of the current row; group g takes q0 + g, q0 + g + G, ...
+  auto accumulate = [&](int q0, int q1) {
+    int q = q0;
+    for (; q + U * G <= q1; q += U * G) {  // full batches: no predicates
+      int c[U];
+      float a[U];
+      Vec<VEC> b[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        c[k] = cs[q + k * G + g];
+        a[k] = vs[q + k * G + g];
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) b[k].load(Bc + (long long)c[k] * p.ldb);
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], b[k].v[v], acc[v]);
+    }
+    if (q < q1) {  // tail batch
+      int c[U];
+      float a[U];
+      Vec<VEC> b[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int idx = q + k * G + g;
+        const bool ok = idx < q1;
+        c[k] = ok ? cs[idx] : -1;
+        a[k] = ok ? vs[idx] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (c[k] >= 0) {
+          b[k].load(Bc + (long long)c[k] * p.ldb);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) b[k].v[v] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], b[k].v[v], acc[v]);
+    }
+  };
+
+  // combine the G partial sums of a row (warp-shuffle reduction); result valid in group 0
+  auto reduce_groups = [&]() {
+    if (G > 1) {
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += __shfl_xor_sync(FULL, acc[v], o);
+    }
+  };
+  auto emit = [&](float* dst) {  // store acc (group 0 lanes) and clear it
+    if (writer) {
       Vec<VEC> o;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
-      if (head) {
-        o.store(p.pieces + (size_t)(2 * t) * p.N + col0);
-        if (gl == 0) *p.split_flag = 1;
-      } else {
-        o.store_stream(p.C + (long long)r * p.ldc + col0);
-      }
+      o.store_stream(dst);
     }
-    head = false;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   };
 
-  int n_iter = (j1 - j0 + LPR - 1) / LPR;
-  if (LPR < 32) {
-#pragma unroll
-    for (int o = 16; o >= LPR; o >>= 1) n_iter = max(n_iter, __shfl_xor_sync(FULL, n_iter, o));
-  }
-
-  for (int it = 0; it < n_iter; ++it) {
-    const int chunk = j0 + it * LPR;
-    const int idx = chunk + gl;
-    int creg = 0;
-    float vreg = 0.f;
-    if (idx < j1) {
-      if (STAGE) {
-        creg = s_col[idx - a0];
-        vreg = s_val[idx - a0];
-      } else {
-        creg = __ldg(p.col + idx);
-        vreg = __ldg(p.val + idx);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < LPR; b += C::U) {
-      Vec<VEC> bv[C::U];
-      float vv[C::U];
-      // phase 1: U independent gathers of B rows
-#pragma unroll
-      for (int k = 0; k < C::U; ++k) {
-        const int c = __shfl_sync(FULL, creg, b + k, LPR);
-        vv[k] = __shfl_sync(FULL, vreg, b + k, LPR);
-        if (active && (chunk + b + k) < j1) {
-          bv[k].load(Bc + (long long)c * p.ldb);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) bv[k].v[v] = 0.f;
-        }
-      }
-      // phase 2: consume in CSR order, closing rows as their ends are reached
-#pragma unroll
-      for (int k = 0; k < C::U; ++k) {
-        const int pp = chunk + b + k;
-        if (pp < j1) {
-          while (pp == row_end) {
-            flush(row);
-            ++row;
-            row_end = __ldg(p.row_ptr + row + 1);
-          }
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] = fmaf(vv[k], bv[k].v[v], acc[v]);
-        }
-      }
-    }
-  }
-
-  // rows that end at or before the task end (the current one, then empty rows)
+  // rows that END inside this task: [row, i1).  Row ends are fetched 32 at a time.
+  int rbase = row;
+  int rcache = (rbase + lane < p.M) ? __ldg(p.row_ptr + rbase + lane + 1) : 0;
   while (row < i1) {
-    flush(row);
+    if (row - rbase >= 32) {
+      rbase = row;
+      rcache = (rbase + lane < p.M) ? __ldg(p.row_ptr + rbase + lane + 1) : 0;
+    }
+    const int re = __shfl_sync(FULL, rcache, row - rbase);
+    accumulate(pos, re);
+    pos = re;
+    reduce_groups();
+    if (head) {
+      emit(p.pieces + (size_t)(2 * (size_t)t) * p.N + col0);
+      if (lane == 0) *p.split_flag = 1;
+      head = false;
+    } else {
+      emit(p.C + (long long)row * p.ldc + col0);
+    }
     ++row;
   }
-  // partial last row (only when a heavy row is split at the task end)
-  if (i1 < p.M && j1 > j0 && j1 > __ldg(p.row_ptr + i1)) {
-    if (active) {
-      Vec<VEC> o;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
-      o.store(p.pieces + (size_t)(2 * t + (head ? 0 : 1)) * p.N + col0);
-      if (gl == 0) *p.split_flag = 1;
-    }
+  // partial last row: a heavy row that goes on into the next task
+  if (i1 < p.M && j1 > pos) {
+    accumulate(pos, j1);
+    reduce_groups();
+    emit(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
+    if (lane == 0) *p.split_flag = 1;
   }
 }
 
 // Adds up the pieces of every split row in task order and writes the row of C.
-// One virtual warp per interior task boundary; exits at once when no row was split.
-template <int LPR, int VEC>
+// One group of LPR lanes per interior task boundary; exits at once when no row was split.
+template <int VEC, int LPR>
 __global__ void __launch_bounds__(256)
-spmm_fixup_kernel(FwdParams p, int W, int heavy, int n_tasks) {
+spmm_fixup_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int n_tasks) {
   if (*reinterpret_cast<volatile int*>(p.split_flag) == 0) return;
   constexpr int GROUPS_PER_CTA = 256 / LPR;
-  const int grp = threadIdx.x / LPR, gl = threadIdx.x % LPR;
+  const int grp = threadIdx.x / LPR, l = threadIdx.x % LPR;
   const long long b = 1 + (long long)blockIdx.x * GROUPS_PER_CTA + grp;
   if (b >= n_tasks) return;
-  const Boundary bd = merge_path_boundary(p.row_ptr, p.M, p.nnz, b * (long long)W, heavy);
+  const Boundary bd = bnd[b];
   const int i = bd.row;
   if (i >= p.M) return;
   const int rs = __ldg(p.row_ptr + i);
-  if (bd.nz <= rs) return;  // boundary is at a row start: nothing split here
-  const Boundary nb = merge_path_boundary(p.row_ptr, p.M, p.nnz, (b + 1) * (long long)W, heavy);
-  if (nb.row == i) return;  // the row goes on; the boundary where it ends does the sum
+  if (bd.nz <= rs) return;       // boundary is at a row start: nothing split here
+  if (bnd[b + 1].row == i) return;  // the row goes on; the boundary where it ends does the sum
   const long long t_first = ((long long)rs + i) / W;
-  const int col0 = blockIdx.y * (LPR * VEC) + gl * VEC;
+  const int col0 = blockIdx.y * (LPR * VEC) + l * VEC;
   if (col0 >= p.N) return;
   Vec<VEC> sum, x;
   sum.load(p.pieces + (size_t)(2 * t_first + 1) * p.N + col0);
@@ -217,74 +227,6 @@ spmm_fixup_kernel(FwdParams p, int W, int heavy, int n_tasks) {
   sum.store_stream(p.C + (long long)i * p.ldc + col0);
 }
 
-struct Pick {
-  int vec, lpr, W, heavy, n_tasks, slabs;
-};
-
-Pick pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2) {
-  Pick k;
-  k.vec = (N % 4 == 0 && aligned4) ? 4 : ((N % 2 == 0 && aligned2) ? 2 : 1);
-  if (k.vec == 4) {
-    k.lpr = 4;
-    while (k.lpr < 32 && (long long)k.lpr * 4 < N) k.lpr <<= 1;
-  } else {
-    k.lpr = 32;
-  }
-  int W = options().items_per_task;
-  if (W <= 0) W = (k.lpr == 32) ? 256 : 128;
-  W = (W + 31) & ~31;
-  if (W > 2048) W = 2048;
-  {  // keep the staged segment of a CTA within ~160 KB of shared memory
-    const int groups = 32 / k.lpr, warps = (k.lpr >= 16) ? 8 : 4;
-    while (W > 128 && (size_t)smem_capacity(warps * groups, W, W) * 8 > 160 * 1024) W >>= 1;
-  }
-  k.W = W;
-  k.heavy = W;
-  long long items = M + nnz;
-  k.n_tasks = (int)((items + W - 1) / W);
-  if (k.n_tasks < 1) k.n_tasks = 1;
-  k.slabs = (int)((N + (long long)k.lpr * k.vec - 1) / ((long long)k.lpr * k.vec));
-  return k;
-}
-
-template <int LPR, int VEC, bool STAGE>
-int launch_one(const FwdParams& p, const Pick& k, cudaStream_t s) {
-  using C = Cfg<LPR>;
-  const int cap = smem_capacity(C::TASKS, k.W, k.heavy);
-  constexpr int BND_BYTES = ((C::TASKS + 1) * (int)sizeof(Boundary) + 15) & ~15;
-  size_t smem = 16 + BND_BYTES + (STAGE ? (size_t)cap * 8 : 0);
-  auto kern = spmm_fwd_kernel<LPR, VEC, STAGE>;
-  if (smem > 48 * 1024) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  dim3 grid((unsigned)((k.n_tasks + C::TASKS - 1) / C::TASKS), (unsigned)k.slabs);
-  kern<<<grid, C::WARPS * 32, smem, s>>>(p, k.W, k.heavy, k.n_tasks);
-  B200_LAUNCH_OK("spmm_fwd_kernel");
-  if (k.n_tasks > 1) {
-    constexpr int GROUPS_PER_CTA = 256 / LPR;
-    dim3 fgrid((unsigned)((k.n_tasks - 1 + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA), (unsigned)k.slabs);
-    spmm_fixup_kernel<LPR, VEC><<<fgrid, 256, 0, s>>>(p, k.W, k.heavy, k.n_tasks);
-    B200_LAUNCH_OK("spmm_fixup_kernel");
-  }
-  return B200_OK;
-}
-
-template <bool STAGE>
-int dispatch(const FwdParams& p, const Pick& k, cudaStream_t s) {
-  if (k.vec == 4) {
-    switch (k.lpr) {
-      case 4: return launch_one<4, 4, STAGE>(p, k, s);
-      case 8: return launch_one<8, 4, STAGE>(p, k, s);
-      case 16: return launch_one<16, 4, STAGE>(p, k, s);
-      default: return launch_one<32, 4, STAGE>(p, k, s);
-    }
-  }
-  if (k.vec == 2) return launch_one<32, 2, STAGE>(p, k, s);
-  return launch_one<32, 1, STAGE>(p, k, s);
-}
-
-inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
-
 __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
   long long n = (long long)M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -293,21 +235,88 @@ __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
   }
 }
 
+inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <int VEC, int LPR, bool STAGE>
+int launch_one(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+  constexpr int U = (32 / LPR >= 4) ? 4 : 8;
+  const int cap = smem_capacity(k.W, k.heavy);
+  constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
+  const size_t smem = 16 + BND_BYTES + (STAGE ? (size_t)cap * 8 : 0);
+  auto kern = spmm_fwd_kernel<VEC, LPR, U, STAGE>;
+  if (smem > 48 * 1024) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  dim3 grid((unsigned)((k.n_tasks + WARPS - 1) / WARPS), (unsigned)k.slabs);
+  kern<<<grid, WARPS * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
+  B200_LAUNCH_OK("spmm_fwd_kernel");
+  if (k.n_tasks > 1 && k.may_split) {
+    constexpr int GROUPS_PER_CTA = 256 / LPR;
+    dim3 fgrid((unsigned)((k.n_tasks - 1 + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA), (unsigned)k.slabs);
+    spmm_fixup_kernel<VEC, LPR><<<fgrid, 256, 0, s>>>(p, bnd, k.W, k.n_tasks);
+    B200_LAUNCH_OK("spmm_fixup_kernel");
+  }
+  return B200_OK;
+}
+
+template <bool STAGE>
+int dispatch(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+#define B200_CASE(V, L) \
+  if (k.vec == V && k.lpr == L) return launch_one<V, L, STAGE>(p, k, bnd, s)
+  B200_CASE(4, 32); B200_CASE(4, 16); B200_CASE(4, 8); B200_CASE(4, 4);
+  B200_CASE(2, 32); B200_CASE(2, 16); B200_CASE(2, 8); B200_CASE(2, 4);
+  B200_CASE(1, 32); B200_CASE(1, 16); B200_CASE(1, 8); B200_CASE(1, 4);
+#undef B200_CASE
+  set_error("internal: no kernel for vec %d lpr %d", k.vec, k.lpr);
+  return B200_ERR_INVALID;
+}
+
 }  // namespace
 
-size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
-  // sized for the smallest task size the launcher may pick (W >= 32 after rounding,
-  // but auto picks >= 128); keep in sync with pick().
+// Lane layout and task size for a problem; depends only on (M, nnz, N, alignment), so a plan
+// can cache the boundaries computed for it.
+FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2, int max_row) {
+  FwdPick k;
+  k.vec = (N % 4 == 0 && aligned4) ? 4 : ((N % 2 == 0 && aligned2) ? 2 : 1);
+  k.lpr = 4;
+  while (k.lpr < 32 && (long long)k.lpr * k.vec < N) k.lpr <<= 1;
   int W = options().items_per_task;
-  if (W <= 0 || W > 128) W = 128;  // pick() never goes below min(128, option)
+  if (W <= 0) W = 256;
+  W = (W + 31) & ~31;
+  if (W > 2048) W = 2048;
+  while (W > 128 && (size_t)smem_capacity(W, W) * 8 > 160 * 1024) W >>= 1;
+  k.W = W;
+  k.heavy = W;
+  const long long items = M + nnz;
+  k.n_tasks = (int)((items + W - 1) / W);
+  if (k.n_tasks < 1) k.n_tasks = 1;
+  k.slabs = (int)((N + (long long)k.lpr * k.vec - 1) / ((long long)k.lpr * k.vec));
+  k.may_split = (max_row < 0) || (max_row > k.heavy);
+  return k;
+}
+
+size_t fwd_bounds_bytes(int n_tasks) { return (((size_t)n_tasks + 2) * sizeof(Boundary) + 255) & ~(size_t)255; }
+
+size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
+  // sized for the smallest task size the launcher may pick; keep in sync with fwd_pick().
+  int W = options().items_per_task;
+  if (W <= 0 || W > 128) W = 128;
   W = (W + 31) & ~31;
   long long n_tasks = (M + nnz + W - 1) / W;
   if (n_tasks < 1) n_tasks = 1;
-  return 256 + (size_t)2 * (size_t)n_tasks * (size_t)N * sizeof(float);
+  return 256 + fwd_bounds_bytes((int)n_tasks) + (size_t)2 * (size_t)n_tasks * (size_t)N * sizeof(float);
 }
 
+int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, Boundary* out, cudaStream_t s) {
+  const int n = k.n_tasks + 1;
+  partition_kernel<<<(n + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, k.W, k.heavy, k.n_tasks, out);
+  B200_LAUNCH_OK("partition_kernel");
+  return B200_OK;
+}
+
+// workspace layout: [split flag, 256 B][boundaries (unless cached_bnd)][pieces 2 * n_tasks * N]
 int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_bytes,
-                        cudaStream_t s) {
+                        const Boundary* cached_bnd, const FwdPick* cached_pick, cudaStream_t s) {
   FwdParams p = pin;
   if (p.M == 0 || p.N == 0) return B200_OK;
   if (p.nnz == 0) {  // all rows empty: C = 0
@@ -318,8 +327,13 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
   }
   const bool a4 = is_aligned(p.B, 16) && is_aligned(p.C, 16) && (p.ldb % 4 == 0) && (p.ldc % 4 == 0);
   const bool a2 = is_aligned(p.B, 8) && is_aligned(p.C, 8) && (p.ldb % 2 == 0) && (p.ldc % 2 == 0);
-  const Pick k = pick(p.M, p.nnz, p.N, a4, a2);
-  const size_t need = 256 + (size_t)2 * (size_t)k.n_tasks * (size_t)p.N * sizeof(float);
+  FwdPick k = fwd_pick(p.M, p.nnz, p.N, a4, a2, -1);
+  const bool use_cache = cached_bnd != nullptr && cached_pick != nullptr && cached_pick->W == k.W &&
+                         cached_pick->heavy == k.heavy && cached_pick->n_tasks == k.n_tasks;
+  if (use_cache) k.may_split = cached_pick->may_split;
+  const size_t bnd_bytes = use_cache ? 0 : fwd_bounds_bytes(k.n_tasks);
+  const size_t pieces_bytes = k.may_split ? (size_t)2 * (size_t)k.n_tasks * (size_t)p.N * sizeof(float) : 0;
+  const size_t need = 256 + bnd_bytes + pieces_bytes;
   if (workspace == nullptr) {
     void* w = nullptr;
     int rc = get_scratch(need, &w);
@@ -335,12 +349,20 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
     set_error("workspace must be 16-byte aligned");
     return B200_ERR_INVALID;
   }
-  p.split_flag = reinterpret_cast<int*>(workspace);
-  p.pieces = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
-  B200_CUDA_OK(cudaMemsetAsync(p.split_flag, 0, sizeof(int), s));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  p.split_flag = reinterpret_cast<int*>(ws);
+  const Boundary* bnd = cached_bnd;
+  if (!use_cache) {
+    Boundary* b = reinterpret_cast<Boundary*>(ws + 256);
+    int rc = launch_partition(p.row_ptr, p.M, p.nnz, k, b, s);
+    if (rc != B200_OK) return rc;
+    bnd = b;
+  }
+  p.pieces = reinterpret_cast<float*>(ws + 256 + bnd_bytes);
+  if (k.may_split) B200_CUDA_OK(cudaMemsetAsync(p.split_flag, 0, sizeof(int), s));
   const int want_stage = (p.stage >= 0) ? p.stage : options().stage_mode;
   const bool stage = want_stage == 1 && is_aligned(p.col, 16) && is_aligned(p.val, 16);
-  return stage ? dispatch<true>(p, k, s) : dispatch<false>(p, k, s);
+  return stage ? dispatch<true>(p, k, bnd, s) : dispatch<false>(p, k, bnd, s);
 }
 
 }  // namespace b200

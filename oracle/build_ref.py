@@ -6,7 +6,7 @@ history: the sources are compiled where they lie and only binaries land in oracl
 
   oracle/_ref/custom_mm.so   the reference's pybind module (src/custom_mm.cpp, baseline_mm.cu,
                              sparse_mm.cu, naive_sparse_mm.cu — the file list of src/setup.py:12-17)
-  oracle/_ref/matmuls.pyc    byte-compiled /root/reference/matmuls.py (its autograd wrappers)
+  oracle/_ref/matmuls_ref.bin    byte-compiled /root/reference/matmuls.py (its autograd wrappers)
 
 The single deviation from `python setup.py install` in src/: CUDA 12 removed the enum
 CUSPARSE_MM_ALG_DEFAULT used at src/baseline_mm.cu:308,313, so the build passes
@@ -32,7 +32,7 @@ SOURCES = ["custom_mm.cpp", "baseline_mm.cu", "sparse_mm.cu", "naive_sparse_mm.c
 
 
 def available() -> bool:
-    return (OUT / "custom_mm.so").exists() and (OUT / "matmuls.pyc").exists()
+    return (OUT / "custom_mm.so").exists() and (OUT / "matmuls_ref.bin").exists()
 
 
 def build(force: bool = False, verbose: bool = True) -> bool:
@@ -80,9 +80,9 @@ def build(force: bool = False, verbose: bool = True) -> bool:
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"reference link failed:\n{r.stdout[-3000:]}")
-    py_compile.compile(str(REF / "matmuls.py"), cfile=str(OUT / "matmuls.pyc"), doraise=True)
+    py_compile.compile(str(REF / "matmuls.py"), cfile=str(OUT / "matmuls_ref.bin"), doraise=True)
     if verbose:
-        print(f"[build_ref] wrote {OUT}/custom_mm.so and matmuls.pyc", flush=True)
+        print(f"[build_ref] wrote {OUT}/custom_mm.so and matmuls_ref.bin", flush=True)
     return True
 
 
@@ -102,7 +102,7 @@ def load():
         cm = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(cm)
         sys.modules["custom_mm"] = cm  # the reference's matmuls does `import custom_mm`
-        loader = importlib.machinery.SourcelessFileLoader("matmuls", str(OUT / "matmuls.pyc"))
+        loader = importlib.machinery.SourcelessFileLoader("matmuls", str(OUT / "matmuls_ref.bin"))
         spec2 = importlib.util.spec_from_loader("matmuls", loader)
         mm = importlib.util.module_from_spec(spec2)
         loader.exec_module(mm)
