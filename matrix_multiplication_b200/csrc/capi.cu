@@ -242,6 +242,7 @@ int b200_spmm_csr_forward_flags(const int32_t* d_row_ptr, const int32_t* d_col_i
   if (rc) return rc;
   B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
   B200_REQUIRE(ldb >= N && ldc >= N, "leading dimension smaller than N");
+  B200_REQUIRE(ldb < 0x7fffffffLL && ldc < 0x7fffffffLL, "leading dimension out of range");
   if (M == 0 || N == 0) return B200_OK;
   B200_REQUIRE(d_row_ptr != nullptr && d_C != nullptr, "null row_ptr / C");
   B200_REQUIRE(nnz == 0 || (d_col_ind != nullptr && d_val != nullptr && d_B != nullptr), "null col/val/B");
@@ -399,6 +400,7 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
                      cudaStream_t s) {
   B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
   B200_REQUIRE(ldb >= N && ldc >= N, "leading dimension smaller than N");
+  B200_REQUIRE(ldb < 0x7fffffffLL && ldc < 0x7fffffffLL, "leading dimension out of range");
   if (M == 0 || N == 0) return B200_OK;
   B200_REQUIRE(d_C != nullptr && (p->nnz == 0 || d_B != nullptr), "null B / C");
   int rc = plan_ensure_bounds(p, side, row_ptr, M, max_row, N, s);

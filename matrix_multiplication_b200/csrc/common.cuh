@@ -89,6 +89,9 @@ __host__ __device__ __forceinline__ Boundary merge_path_boundary(
 #else
   int rs = row_ptr[i], re = row_ptr[i + 1];
 #endif
+  // all non-zeros of row i consumed, only its row-end item left: the row is complete.  (A row's last
+  // non-zero and its row end are therefore always in the same task.)
+  if (j >= re) return Boundary{i + 1, re};
   if (j > rs && (re - rs) <= heavy) j = rs;
   return Boundary{i, j};
 }

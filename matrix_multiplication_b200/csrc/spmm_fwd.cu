@@ -29,8 +29,10 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 8;  // warps (= tasks) per CTA
 
 __host__ __device__ inline int smem_capacity(int W, int heavy) {
-  return ((WARPS * W + heavy + 8) + 3) & ~3;  // non-zeros a CTA may have to stage
+  return ((WARPS * W + heavy + 24) + 7) & ~7;  // non-zeros a CTA may have to stage
 }
+
+__host__ __device__ inline int mask_words(int cap) { return ((cap >> 3) + 4 + 3) & ~3; }  // keeps s_col 16-byte aligned
 
 __global__ void __launch_bounds__(256)
 partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int heavy, int n_tasks,
@@ -102,6 +104,9 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
+  const unsigned ldb = (unsigned)p.ldb;  // < 2^31 (checked by the host): one IMAD.WIDE.U32 per gather
+  auto brow = [&](int c) { return Bc + (unsigned long long)(unsigned)c * ldb; };
+
   // acc += sum over non-zeros [q0, q1) of the current row; group g takes q0 + g, q0 + g + G, ...
   auto accumulate = [&](int q0, int q1) {
     int q = q0;
@@ -115,7 +120,7 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
         a[k] = vs[q + k * G + g];
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k) b[k].load(Bc + (long long)c[k] * p.ldb);
+      for (int k = 0; k < U; ++k) b[k].load(brow(c[k]));
 #pragma unroll
       for (int k = 0; k < U; ++k)
 #pragma unroll
@@ -135,7 +140,7 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         if (c[k] >= 0) {
-          b[k].load(Bc + (long long)c[k] * p.ldb);
+          b[k].load(brow(c[k]));
         } else {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) b[k].v[v] = 0.f;
@@ -194,6 +199,173 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
     accumulate(pos, j1);
     reduce_groups();
     emit(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
+    if (lane == 0) *p.split_flag = 1;
+  }
+}
+
+// ---- flat kernel (one lane group: N >= 32 or so) ------------------------------------------------
+// The warp walks its task's non-zeros in aligned chunks of 8 regardless of row boundaries: per chunk
+// four 16-byte broadcast reads of the staged (col, val) segment, 8 independent B-row gathers, 8*VEC
+// FMAs per lane.  Row ends are a per-chunk bit mask (built once per CTA from row_ptr, together with
+// the row id stored at each row-end position), so the common chunk without a row end runs
+// straight-line code and a row end costs one store.  Empty rows are zero-filled by the CTA up front.
+template <int VEC, bool TMA>
+__global__ void __launch_bounds__(WARPS * 32)
+spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy, int n_tasks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [mbar 16B][Boundary x (WARPS+1), 80B][mask words CAP/8 + 4][s_col CAP][s_val CAP][s_rowend CAP]
+  const int cap = smem_capacity(W, heavy);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  Boundary* bnd_s = reinterpret_cast<Boundary*>(smem_raw + 16);
+  constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
+  unsigned* s_mask = reinterpret_cast<unsigned*>(smem_raw + 16 + BND_BYTES);
+  int* s_col = reinterpret_cast<int*>(s_mask + mask_words(cap));
+  float* s_val = reinterpret_cast<float*>(s_col + cap);
+  int* s_rowend = reinterpret_cast<int*>(s_val + cap);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int task0 = blockIdx.x * WARPS;
+
+  if (tid <= WARPS) bnd_s[tid] = bnd[min(task0 + tid, n_tasks)];
+  if (TMA && tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int a0 = bnd_s[0].nz & ~7;  // staged window starts on a chunk (32-byte) boundary
+  const int je = bnd_s[WARPS].nz;
+  const int n_bulk = TMA ? ((je - a0) & ~3) : 0;
+  if (TMA && tid == 0 && n_bulk > 0) {
+    mbar_expect_tx(bar, (uint32_t)n_bulk * 8u);
+    tma_bulk_g2s(s_col, p.col + a0, (uint32_t)n_bulk * 4u, bar);
+    tma_bulk_g2s(s_val, p.val + a0, (uint32_t)n_bulk * 4u, bar);
+  }
+  for (int q = a0 + n_bulk + tid; q < je; q += blockDim.x) {  // fringe (or everything when !TMA)
+    s_col[q - a0] = __ldg(p.col + q);
+    s_val[q - a0] = __ldg(p.val + q);
+  }
+  for (int i = tid; i < ((je - a0 + 7) >> 3); i += blockDim.x) s_mask[i] = 0u;
+  __syncthreads();
+
+  const int col0 = blockIdx.y * (32 * VEC) + lane * VEC;
+  const bool active = col0 < p.N;
+
+  // rows that end inside this CTA: mark the row ends, zero-fill the empty rows
+  {
+    const int R0 = bnd_s[0].row, R1 = bnd_s[WARPS].row;
+    for (int base = R0 + warp * 32; base < R1; base += WARPS * 32) {
+      const int r = base + lane;
+      int rs = 0, re = 0;
+      if (r < R1) {
+        rs = __ldg(p.row_ptr + r);
+        re = __ldg(p.row_ptr + r + 1);
+      }
+      if (re > rs) {
+        const int pos = re - 1 - a0;
+        atomicOr(&s_mask[pos >> 3], 1u << (pos & 7));
+        s_rowend[pos] = r;
+      }
+      unsigned em = __ballot_sync(FULL, r < R1 && re == rs);
+      while (em) {
+        const int b = __ffs(em) - 1;
+        em &= em - 1;
+        if (active) {
+          Vec<VEC> z;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) z.v[v] = 0.f;
+          z.store_stream(p.C + (long long)(base + b) * p.ldc + col0);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (TMA && n_bulk > 0) mbar_wait(bar, 0);
+
+  // ---- this warp's task ---------------------------------------------------------------
+  const int t = task0 + warp;
+  const Boundary b0 = bnd_s[warp], b1 = bnd_s[warp + 1];
+  const int j0 = b0.nz, j1 = b1.nz;
+  if (j1 <= j0) return;  // no non-zeros in this task
+  bool head = j0 > __ldg(p.row_ptr + b0.row);  // the first row continues a split heavy row
+
+  const float* Bc = p.B + (active ? col0 : 0);  // inactive lanes gather column 0 (valid, never stored)
+  const unsigned ldb = (unsigned)p.ldb;
+  float acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+
+  auto emit = [&](int off) {  // the non-zero at staged offset `off` is the last one of its row
+    float* dst;
+    if (head) {
+      dst = p.pieces + (size_t)(2 * (size_t)t) * p.N + col0;
+      if (lane == 0) *p.split_flag = 1;
+      head = false;
+    } else {
+      dst = p.C + (long long)s_rowend[off] * p.ldc + col0;
+    }
+    if (active) {
+      Vec<VEC> o;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
+      o.store_stream(dst);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  };
+
+  for (int c0 = j0 & ~7; c0 < j1; c0 += 8) {
+    const int off = c0 - a0;
+    unsigned m = s_mask[off >> 3];
+    const int4 ca = *reinterpret_cast<const int4*>(s_col + off);
+    const int4 cb = *reinterpret_cast<const int4*>(s_col + off + 4);
+    const float4 va = *reinterpret_cast<const float4*>(s_val + off);
+    const float4 vb = *reinterpret_cast<const float4*>(s_val + off + 4);
+    const int c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    float a[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    Vec<VEC> b[8];
+    if (c0 >= j0 && c0 + 8 <= j1) {  // interior chunk: no predicates
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[k].load(Bc + (unsigned long long)(unsigned)c[k] * ldb);
+    } else {  // first / last chunk of the task: elements outside [j0, j1) belong to other tasks
+      const int lo = max(j0 - c0, 0), hi = min(j1 - c0, 8);
+      const unsigned vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      m &= vm;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if ((vm >> k) & 1u) {
+          b[k].load(Bc + (unsigned long long)(unsigned)c[k] * ldb);
+        } else {
+          a[k] = 0.f;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) b[k].v[v] = 0.f;
+        }
+      }
+    }
+    if (m == 0u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], b[k].v[v], acc[v]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], b[k].v[v], acc[v]);
+        if ((m >> k) & 1u) emit(off + k);
+      }
+    }
+  }
+  // the task ends inside a (heavy) row: its partial sum is a piece
+  const int last = j1 - 1 - a0;
+  if (((s_mask[last >> 3] >> (last & 7)) & 1u) == 0u) {
+    if (active) {
+      Vec<VEC> o;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
+      o.store_stream(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
+    }
     if (lane == 0) *p.split_flag = 1;
   }
 }
@@ -259,13 +431,39 @@ int launch_one(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaSt
   return B200_OK;
 }
 
+template <int VEC, bool TMA>
+int launch_flat(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+  const int cap = smem_capacity(k.W, k.heavy);
+  constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
+  const size_t smem = 16 + BND_BYTES + (size_t)mask_words(cap) * 4 + (size_t)cap * 12;
+  auto kern = spmm_flat_kernel<VEC, TMA>;
+  if (smem > 48 * 1024) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  dim3 grid((unsigned)((k.n_tasks + WARPS - 1) / WARPS), (unsigned)k.slabs);
+  kern<<<grid, WARPS * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
+  B200_LAUNCH_OK("spmm_flat_kernel");
+  if (k.n_tasks > 1 && k.may_split) {
+    constexpr int GROUPS_PER_CTA = 256 / 32;
+    dim3 fgrid((unsigned)((k.n_tasks - 1 + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA), (unsigned)k.slabs);
+    spmm_fixup_kernel<VEC, 32><<<fgrid, 256, 0, s>>>(p, bnd, k.W, k.n_tasks);
+    B200_LAUNCH_OK("spmm_fixup_kernel");
+  }
+  return B200_OK;
+}
+
 template <bool STAGE>
 int dispatch(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+  if (k.lpr == 32) {
+    if (k.vec == 4) return launch_flat<4, STAGE>(p, k, bnd, s);
+    if (k.vec == 2) return launch_flat<2, STAGE>(p, k, bnd, s);
+    return launch_flat<1, STAGE>(p, k, bnd, s);
+  }
 #define B200_CASE(V, L) \
   if (k.vec == V && k.lpr == L) return launch_one<V, L, STAGE>(p, k, bnd, s)
-  B200_CASE(4, 32); B200_CASE(4, 16); B200_CASE(4, 8); B200_CASE(4, 4);
-  B200_CASE(2, 32); B200_CASE(2, 16); B200_CASE(2, 8); B200_CASE(2, 4);
-  B200_CASE(1, 32); B200_CASE(1, 16); B200_CASE(1, 8); B200_CASE(1, 4);
+  B200_CASE(4, 16); B200_CASE(4, 8); B200_CASE(4, 4);
+  B200_CASE(2, 16); B200_CASE(2, 8); B200_CASE(2, 4);
+  B200_CASE(1, 16); B200_CASE(1, 8); B200_CASE(1, 4);
 #undef B200_CASE
   set_error("internal: no kernel for vec %d lpr %d", k.vec, k.lpr);
   return B200_ERR_INVALID;
@@ -277,14 +475,22 @@ int dispatch(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStre
 // can cache the boundaries computed for it.
 FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2, int max_row) {
   FwdPick k;
-  k.vec = (N % 4 == 0 && aligned4) ? 4 : ((N % 2 == 0 && aligned2) ? 2 : 1);
-  k.lpr = 4;
-  while (k.lpr < 32 && (long long)k.lpr * k.vec < N) k.lpr <<= 1;
+  const int vmax = (N % 4 == 0 && aligned4) ? 4 : ((N % 2 == 0 && aligned2) ? 2 : 1);
+  if (N >= 24) {
+    // one lane group of 32 lanes (flat kernel): the narrowest vector that covers N in one slab
+    k.vec = 1;
+    while (k.vec < vmax && 32LL * k.vec < N) k.vec <<= 1;
+    k.lpr = 32;
+  } else {
+    k.vec = vmax;
+    k.lpr = 4;
+    while (k.lpr < 16 && (long long)k.lpr * k.vec < N) k.lpr <<= 1;
+  }
   int W = options().items_per_task;
   if (W <= 0) W = 256;
   W = (W + 31) & ~31;
   if (W > 2048) W = 2048;
-  while (W > 128 && (size_t)smem_capacity(W, W) * 8 > 160 * 1024) W >>= 1;
+  while (W > 128 && (size_t)smem_capacity(W, W) * 12 > 160 * 1024) W >>= 1;
   k.W = W;
   k.heavy = W;
   const long long items = M + nnz;
