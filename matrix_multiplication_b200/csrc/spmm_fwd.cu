@@ -28,8 +28,8 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 8;  // warps (= tasks) per CTA
 
-__host__ __device__ inline int smem_capacity(int W, int heavy) {
-  return ((WARPS * W + heavy + 24) + 7) & ~7;  // non-zeros a CTA may have to stage
+__host__ __device__ inline int smem_capacity(int W, int heavy, int warps = WARPS) {
+  return ((warps * W + heavy + 24) + 7) & ~7;  // non-zeros a CTA may have to stage
 }
 
 __host__ __device__ inline int mask_words(int cap) { return ((cap >> 3) + 4 + 3) & ~3; }  // keeps s_col 16-byte aligned
@@ -209,15 +209,15 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
 // FMAs per lane.  Row ends are a per-chunk bit mask (built once per CTA from row_ptr, together with
 // the row id stored at each row-end position), so the common chunk without a row end runs
 // straight-line code and a row end costs one store.  Empty rows are zero-filled by the CTA up front.
-template <int VEC, bool TMA>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int VEC, bool TMA, int NB, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy, int n_tasks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [mbar 16B][Boundary x (WARPS+1), 80B][mask words CAP/8 + 4][s_col CAP][s_val CAP][s_rowend CAP]
-  const int cap = smem_capacity(W, heavy);
+  const int cap = smem_capacity(W, heavy, NW);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   Boundary* bnd_s = reinterpret_cast<Boundary*>(smem_raw + 16);
-  constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
+  constexpr int BND_BYTES = ((NW + 1) * (int)sizeof(Boundary) + 15) & ~15;
   unsigned* s_mask = reinterpret_cast<unsigned*>(smem_raw + 16 + BND_BYTES);
   int* s_col = reinterpret_cast<int*>(s_mask + mask_words(cap));
   float* s_val = reinterpret_cast<float*>(s_col + cap);
@@ -225,9 +225,9 @@ spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int task0 = blockIdx.x * WARPS;
+  const int task0 = blockIdx.x * NW;
 
-  if (tid <= WARPS) bnd_s[tid] = bnd[min(task0 + tid, n_tasks)];
+  if (tid <= NW) bnd_s[tid] = bnd[min(task0 + tid, n_tasks)];
   if (TMA && tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -235,7 +235,7 @@ spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy
   __syncthreads();
 
   const int a0 = bnd_s[0].nz & ~7;  // staged window starts on a chunk (32-byte) boundary
-  const int je = bnd_s[WARPS].nz;
+  const int je = bnd_s[NW].nz;
   const int n_bulk = TMA ? ((je - a0) & ~3) : 0;
   if (TMA && tid == 0 && n_bulk > 0) {
     mbar_expect_tx(bar, (uint32_t)n_bulk * 8u);
@@ -254,8 +254,8 @@ spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy
 
   // rows that end inside this CTA: mark the row ends, zero-fill the empty rows
   {
-    const int R0 = bnd_s[0].row, R1 = bnd_s[WARPS].row;
-    for (int base = R0 + warp * 32; base < R1; base += WARPS * 32) {
+    const int R0 = bnd_s[0].row, R1 = bnd_s[NW].row;
+    for (int base = R0 + warp * 32; base < R1; base += NW * 32) {
       const int r = base + lane;
       int rs = 0, re = 0;
       if (r < R1) {
@@ -315,47 +315,76 @@ spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   };
 
-  for (int c0 = j0 & ~7; c0 < j1; c0 += 8) {
+  // Software pipeline, two chunks deep: the gathers of chunk i+1 are issued before the FMAs of
+  // chunk i, so a warp always has 8..16 B-row loads in flight (bytes in flight, not occupancy, is
+  // what feeds the L1 data path here).
+  // A chunk in flight holds only its 8 gathered B slabs (the values are re-read from shared memory
+  // when they are consumed), so nearly every live register is a load destination.
+  struct Chunk {
+    Vec<VEC> b[8];
+    unsigned m;   // row-end bits of the chunk (restricted to this task)
+    unsigned vm;  // which of the 8 positions belong to this task
+    int off;
+  };
+  auto fetch = [&](Chunk& ch, int c0) {
     const int off = c0 - a0;
-    unsigned m = s_mask[off >> 3];
+    ch.off = off;
+    ch.m = s_mask[off >> 3];
     const int4 ca = *reinterpret_cast<const int4*>(s_col + off);
     const int4 cb = *reinterpret_cast<const int4*>(s_col + off + 4);
-    const float4 va = *reinterpret_cast<const float4*>(s_val + off);
-    const float4 vb = *reinterpret_cast<const float4*>(s_val + off + 4);
     const int c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-    float a[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-    Vec<VEC> b[8];
     if (c0 >= j0 && c0 + 8 <= j1) {  // interior chunk: no predicates
+      ch.vm = 0xffu;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) b[k].load(Bc + (unsigned long long)(unsigned)c[k] * ldb);
+      for (int k = 0; k < 8; ++k) ch.b[k].load(Bc + (unsigned long long)(unsigned)c[k] * ldb);
     } else {  // first / last chunk of the task: elements outside [j0, j1) belong to other tasks
       const int lo = max(j0 - c0, 0), hi = min(j1 - c0, 8);
-      const unsigned vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-      m &= vm;
+      ch.vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      ch.m &= ch.vm;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if ((vm >> k) & 1u) {
-          b[k].load(Bc + (unsigned long long)(unsigned)c[k] * ldb);
+        if ((ch.vm >> k) & 1u) {
+          ch.b[k].load(Bc + (unsigned long long)(unsigned)c[k] * ldb);
         } else {
-          a[k] = 0.f;
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) b[k].v[v] = 0.f;
+          for (int v = 0; v < VEC; ++v) ch.b[k].v[v] = 0.f;
         }
       }
     }
-    if (m == 0u) {
+  };
+  auto consume = [&](const Chunk& ch) {
+    const float4 va = *reinterpret_cast<const float4*>(s_val + ch.off);
+    const float4 vb = *reinterpret_cast<const float4*>(s_val + ch.off + 4);
+    float a[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    if (ch.vm != 0xffu) {  // values of other tasks' positions may be anything (Inf, NaN): mask them
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (!((ch.vm >> k) & 1u)) a[k] = 0.f;
+    }
+    if (ch.m == 0u) {
 #pragma unroll
       for (int k = 0; k < 8; ++k)
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], b[k].v[v], acc[v]);
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], ch.b[k].v[v], acc[v]);
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], b[k].v[v], acc[v]);
-        if ((m >> k) & 1u) emit(off + k);
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(a[k], ch.b[k].v[v], acc[v]);
+        if ((ch.m >> k) & 1u) emit(ch.off + k);
       }
     }
+  };
+  // NB chunks (8 * NB gathers) are issued back to back before their FMAs: bytes in flight per warp,
+  // not occupancy, is what feeds the L2 -> SM path ("binding roof").
+  for (int c0 = j0 & ~7; c0 < j1; c0 += 8 * NB) {
+    Chunk ch[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i == 0 || c0 + 8 * i < j1) fetch(ch[i], c0 + 8 * i);
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i == 0 || c0 + 8 * i < j1) consume(ch[i]);
   }
   // the task ends inside a (heavy) row: its partial sum is a piece
   const int last = j1 - 1 - a0;
@@ -431,17 +460,17 @@ int launch_one(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaSt
   return B200_OK;
 }
 
-template <int VEC, bool TMA>
+template <int VEC, bool TMA, int NB, int NW, int MINB>
 int launch_flat(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
-  const int cap = smem_capacity(k.W, k.heavy);
-  constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
+  const int cap = smem_capacity(k.W, k.heavy, NW);
+  constexpr int BND_BYTES = ((NW + 1) * (int)sizeof(Boundary) + 15) & ~15;
   const size_t smem = 16 + BND_BYTES + (size_t)mask_words(cap) * 4 + (size_t)cap * 12;
-  auto kern = spmm_flat_kernel<VEC, TMA>;
+  auto kern = spmm_flat_kernel<VEC, TMA, NB, NW, MINB>;
   if (smem > 48 * 1024) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  dim3 grid((unsigned)((k.n_tasks + WARPS - 1) / WARPS), (unsigned)k.slabs);
-  kern<<<grid, WARPS * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
+  dim3 grid((unsigned)((k.n_tasks + NW - 1) / NW), (unsigned)k.slabs);
+  kern<<<grid, NW * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_flat_kernel");
   if (k.n_tasks > 1 && k.may_split) {
     constexpr int GROUPS_PER_CTA = 256 / 32;
@@ -452,12 +481,25 @@ int launch_flat(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaS
   return B200_OK;
 }
 
+template <int VEC, bool TMA>
+int launch_flat_nb(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+  // <gathers in flight per warp / 8, warps per CTA, min CTAs per SM>.  Measured on the R-MAT config
+  // (profiles/r1_variant_sweep.md): 4-warp CTAs at 64 registers (8 CTAs/SM) win; deeper per-warp
+  // batches lose more to occupancy and spills than they gain in bytes in flight.
+  switch (options().pipeline) {
+    case 1: return launch_flat<VEC, TMA, 1, 8, 4>(p, k, bnd, s);
+    case 2: return launch_flat<VEC, TMA, 2, 4, 5>(p, k, bnd, s);
+    case 3: return launch_flat<VEC, TMA, 3, 4, 3>(p, k, bnd, s);
+    default: return launch_flat<VEC, TMA, 1, 4, 8>(p, k, bnd, s);
+  }
+}
+
 template <bool STAGE>
 int dispatch(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
   if (k.lpr == 32) {
-    if (k.vec == 4) return launch_flat<4, STAGE>(p, k, bnd, s);
-    if (k.vec == 2) return launch_flat<2, STAGE>(p, k, bnd, s);
-    return launch_flat<1, STAGE>(p, k, bnd, s);
+    if (k.vec == 4) return launch_flat_nb<4, STAGE>(p, k, bnd, s);
+    if (k.vec == 2) return launch_flat_nb<2, STAGE>(p, k, bnd, s);
+    return launch_flat_nb<1, STAGE>(p, k, bnd, s);
   }
 #define B200_CASE(V, L) \
   if (k.vec == V && k.lpr == L) return launch_one<V, L, STAGE>(p, k, bnd, s)
