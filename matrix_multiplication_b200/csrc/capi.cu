@@ -97,7 +97,7 @@ struct b200_plan {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   // cached merge-path boundaries of A (fwd) and A^T (bwd), valid for the FwdPick stored beside them
-  Boundary* bnd[2] = {nullptr, nullptr};
+  void* bnd[2] = {nullptr, nullptr};
   FwdPick pick[2];
   bool bnd_valid[2] = {false, false};
   int t_max_row = -1;
@@ -117,7 +117,7 @@ static int plan_ensure_bounds(b200_plan* p, int side, const int* row_ptr, int M,
   }
   p->bnd_valid[side] = false;
   if (p->nnz == 0 || M == 0) return B200_OK;
-  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->bnd[side]), fwd_bounds_bytes(k.n_tasks)));
+  B200_CUDA_OK(cudaMalloc(&p->bnd[side], fwd_bounds_bytes(k.n_tasks)));
   int rc = launch_partition(row_ptr, M, p->nnz, k, p->bnd[side], s);
   if (rc != B200_OK) return rc;
   p->pick[side] = k;

@@ -189,7 +189,6 @@ struct FwdParams {
   float* C;
   long long ldc;
   float* pieces;   // workspace: [2 * n_tasks][N] partial rows of split heavy rows
-  int* split_flag; // workspace: set to 1 when any piece was written
   int stage;       // 1 / 0 force TMA staging on / off, -1 = process option
 };
 // lane layout + task size chosen for a problem (spmm_fwd.cu)
@@ -200,10 +199,10 @@ struct FwdPick {
 FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2, int max_row);
 size_t fwd_workspace_bytes(long long M, long long nnz, long long N);
 size_t fwd_bounds_bytes(int n_tasks);
-int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, Boundary* out, cudaStream_t s);
+int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s);
 // cached_bnd / cached_pick: boundaries a plan computed earlier for the same (W, heavy, n_tasks); may be null
 int launch_spmm_forward(const FwdParams& p, void* workspace, size_t workspace_bytes,
-                        const Boundary* cached_bnd, const FwdPick* cached_pick, cudaStream_t s);
+                        const void* cached_part, const FwdPick* cached_pick, cudaStream_t s);
 int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
                  const float* B, long long ldb, int N, float* out, cudaStream_t s);
 int launch_transpose(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz,

@@ -34,16 +34,36 @@ __host__ __device__ inline int smem_capacity(int W, int heavy, int warps = WARPS
 
 __host__ __device__ inline int mask_words(int cap) { return ((cap >> 3) + 4 + 3) & ~3; }  // keeps s_col 16-byte aligned
 
+// Partition block in memory: [int fix_count, 12 B pad][Boundary x (n_tasks + 1)][int fix_list x n_tasks].
+// fix_list holds the boundaries b at which a split (heavy) row ENDS in task b: the fix-up kernel sums
+// that row's pieces there.  Everything depends only on (row_ptr, W, heavy): a plan computes it once.
+__host__ __device__ inline const Boundary* part_bnd(const void* part) {
+  return reinterpret_cast<const Boundary*>(reinterpret_cast<const unsigned char*>(part) + 16);
+}
+__host__ __device__ inline const int* part_fix_list(const void* part, int n_tasks) {
+  return reinterpret_cast<const int*>(part_bnd(part) + (n_tasks + 1));
+}
+
 __global__ void __launch_bounds__(256)
 partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int heavy, int n_tasks,
-                 Boundary* __restrict__ out) {
+                 void* __restrict__ part) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t <= n_tasks) out[t] = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, heavy);
+  if (t > n_tasks) return;
+  const Boundary b = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, heavy);
+  const_cast<Boundary*>(part_bnd(part))[t] = b;
+  if (t >= 1 && t < n_tasks && b.row < M && b.nz > __ldg(row_ptr + b.row)) {  // boundary inside a row
+    const Boundary nb = merge_path_boundary(row_ptr, M, nnz, (long long)(t + 1) * W, heavy);
+    if (nb.row != b.row) {  // ... which ends in task t
+      const int slot = atomicAdd(reinterpret_cast<int*>(part), 1);
+      const_cast<int*>(part_fix_list(part, n_tasks))[slot] = t;
+    }
+  }
 }
 
 template <int VEC, int LPR, int U, bool STAGE>
 __global__ void __launch_bounds__(WARPS * 32)
-spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy, int n_tasks) {
+spmm_fwd_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, int n_tasks) {
+  const Boundary* bnd = part_bnd(part);
   constexpr int G = 32 / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [mbar 16B][Boundary (WARPS+1), padded to 80B][s_col CAP][s_val CAP]
@@ -187,7 +207,6 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
     reduce_groups();
     if (head) {
       emit(p.pieces + (size_t)(2 * (size_t)t) * p.N + col0);
-      if (lane == 0) *p.split_flag = 1;
       head = false;
     } else {
       emit(p.C + (long long)row * p.ldc + col0);
@@ -199,7 +218,6 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
     accumulate(pos, j1);
     reduce_groups();
     emit(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
-    if (lane == 0) *p.split_flag = 1;
   }
 }
 
@@ -211,7 +229,8 @@ spmm_fwd_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy,
 // straight-line code and a row end costs one store.  Empty rows are zero-filled by the CTA up front.
 template <int VEC, bool TMA, int NB, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
-spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy, int n_tasks) {
+spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, int n_tasks) {
+  const Boundary* bnd = part_bnd(part);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [mbar 16B][Boundary x (WARPS+1), 80B][mask words CAP/8 + 4][s_col CAP][s_val CAP][s_rowend CAP]
   const int cap = smem_capacity(W, heavy, NW);
@@ -300,7 +319,6 @@ spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy
     float* dst;
     if (head) {
       dst = p.pieces + (size_t)(2 * (size_t)t) * p.N + col0;
-      if (lane == 0) *p.split_flag = 1;
       head = false;
     } else {
       dst = p.C + (long long)s_rowend[off] * p.ldc + col0;
@@ -395,37 +413,33 @@ spmm_flat_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int heavy
       for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
       o.store_stream(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
     }
-    if (lane == 0) *p.split_flag = 1;
   }
 }
 
-// Adds up the pieces of every split row in task order and writes the row of C.
-// One group of LPR lanes per interior task boundary; exits at once when no row was split.
-template <int VEC, int LPR>
+// Adds up the pieces of every split row in task order and writes the row of C.  One warp per
+// (fix-list entry, slab of 32 * VEC columns); exits at once when no row was split.
+template <int VEC>
 __global__ void __launch_bounds__(256)
-spmm_fixup_kernel(FwdParams p, const Boundary* __restrict__ bnd, int W, int n_tasks) {
-  if (*reinterpret_cast<volatile int*>(p.split_flag) == 0) return;
-  constexpr int GROUPS_PER_CTA = 256 / LPR;
-  const int grp = threadIdx.x / LPR, l = threadIdx.x % LPR;
-  const long long b = 1 + (long long)blockIdx.x * GROUPS_PER_CTA + grp;
-  if (b >= n_tasks) return;
-  const Boundary bd = bnd[b];
-  const int i = bd.row;
-  if (i >= p.M) return;
-  const int rs = __ldg(p.row_ptr + i);
-  if (bd.nz <= rs) return;       // boundary is at a row start: nothing split here
-  if (bnd[b + 1].row == i) return;  // the row goes on; the boundary where it ends does the sum
-  const long long t_first = ((long long)rs + i) / W;
-  const int col0 = blockIdx.y * (LPR * VEC) + l * VEC;
+spmm_fixup_kernel(FwdParams p, const void* __restrict__ part, int W, int n_tasks) {
+  const int count = *reinterpret_cast<const int*>(part);
+  const Boundary* bnd = part_bnd(part);
+  const int* list = part_fix_list(part, n_tasks);
+  const int lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * (32 * VEC) + lane * VEC;
   if (col0 >= p.N) return;
-  Vec<VEC> sum, x;
-  sum.load(p.pieces + (size_t)(2 * t_first + 1) * p.N + col0);
-  for (long long t = t_first + 1; t <= b; ++t) {
-    x.load(p.pieces + (size_t)(2 * t) * p.N + col0);
+  for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < count; e += gridDim.x * 8) {
+    const int b = __ldg(list + e);
+    const int i = bnd[b].row;
+    const long long t_first = ((long long)__ldg(p.row_ptr + i) + i) / W;
+    Vec<VEC> sum, x;
+    sum.load(p.pieces + (size_t)(2 * t_first + 1) * p.N + col0);
+    for (long long t = t_first + 1; t <= b; ++t) {
+      x.load(p.pieces + (size_t)(2 * t) * p.N + col0);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
+      for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
+    }
+    sum.store_stream(p.C + (long long)i * p.ldc + col0);
   }
-  sum.store_stream(p.C + (long long)i * p.ldc + col0);
 }
 
 __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
@@ -438,8 +452,18 @@ __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
 
 inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+template <int VEC>
+int launch_fixup(const FwdParams& p, const FwdPick& k, const void* part, cudaStream_t s) {
+  if (k.n_tasks <= 1 || !k.may_split) return B200_OK;
+  const int slabs = (p.N + 32 * VEC - 1) / (32 * VEC);
+  dim3 fgrid((unsigned)std::min(148 * 2, (k.n_tasks + 7) / 8), (unsigned)slabs);
+  spmm_fixup_kernel<VEC><<<fgrid, 256, 0, s>>>(p, part, k.W, k.n_tasks);
+  B200_LAUNCH_OK("spmm_fixup_kernel");
+  return B200_OK;
+}
+
 template <int VEC, int LPR, bool STAGE>
-int launch_one(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+int launch_one(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
   constexpr int U = (32 / LPR >= 4) ? 4 : 8;
   const int cap = smem_capacity(k.W, k.heavy);
   constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
@@ -451,17 +475,11 @@ int launch_one(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaSt
   dim3 grid((unsigned)((k.n_tasks + WARPS - 1) / WARPS), (unsigned)k.slabs);
   kern<<<grid, WARPS * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_fwd_kernel");
-  if (k.n_tasks > 1 && k.may_split) {
-    constexpr int GROUPS_PER_CTA = 256 / LPR;
-    dim3 fgrid((unsigned)((k.n_tasks - 1 + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA), (unsigned)k.slabs);
-    spmm_fixup_kernel<VEC, LPR><<<fgrid, 256, 0, s>>>(p, bnd, k.W, k.n_tasks);
-    B200_LAUNCH_OK("spmm_fixup_kernel");
-  }
-  return B200_OK;
+  return launch_fixup<VEC>(p, k, bnd, s);
 }
 
 template <int VEC, bool TMA, int NB, int NW, int MINB>
-int launch_flat(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+int launch_flat(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
   const int cap = smem_capacity(k.W, k.heavy, NW);
   constexpr int BND_BYTES = ((NW + 1) * (int)sizeof(Boundary) + 15) & ~15;
   const size_t smem = 16 + BND_BYTES + (size_t)mask_words(cap) * 4 + (size_t)cap * 12;
@@ -472,17 +490,11 @@ int launch_flat(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaS
   dim3 grid((unsigned)((k.n_tasks + NW - 1) / NW), (unsigned)k.slabs);
   kern<<<grid, NW * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_flat_kernel");
-  if (k.n_tasks > 1 && k.may_split) {
-    constexpr int GROUPS_PER_CTA = 256 / 32;
-    dim3 fgrid((unsigned)((k.n_tasks - 1 + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA), (unsigned)k.slabs);
-    spmm_fixup_kernel<VEC, 32><<<fgrid, 256, 0, s>>>(p, bnd, k.W, k.n_tasks);
-    B200_LAUNCH_OK("spmm_fixup_kernel");
-  }
-  return B200_OK;
+  return launch_fixup<VEC>(p, k, bnd, s);
 }
 
 template <int VEC, bool TMA>
-int launch_flat_nb(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+int launch_flat_nb(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
   // <gathers in flight per warp / 8, warps per CTA, min CTAs per SM>.  Measured on the R-MAT config
   // (profiles/r1_variant_sweep.md): 4-warp CTAs at 64 registers (8 CTAs/SM) win; deeper per-warp
   // batches lose more to occupancy and spills than they gain in bytes in flight.
@@ -495,7 +507,7 @@ int launch_flat_nb(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cu
 }
 
 template <bool STAGE>
-int dispatch(const FwdParams& p, const FwdPick& k, const Boundary* bnd, cudaStream_t s) {
+int dispatch(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
   if (k.lpr == 32) {
     if (k.vec == 4) return launch_flat_nb<4, STAGE>(p, k, bnd, s);
     if (k.vec == 2) return launch_flat_nb<2, STAGE>(p, k, bnd, s);
@@ -543,7 +555,9 @@ FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool al
   return k;
 }
 
-size_t fwd_bounds_bytes(int n_tasks) { return (((size_t)n_tasks + 2) * sizeof(Boundary) + 255) & ~(size_t)255; }
+size_t fwd_bounds_bytes(int n_tasks) {
+  return (16 + ((size_t)n_tasks + 2) * sizeof(Boundary) + ((size_t)n_tasks + 1) * sizeof(int) + 255) & ~(size_t)255;
+}
 
 size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
   // sized for the smallest task size the launcher may pick; keep in sync with fwd_pick().
@@ -552,19 +566,20 @@ size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
   W = (W + 31) & ~31;
   long long n_tasks = (M + nnz + W - 1) / W;
   if (n_tasks < 1) n_tasks = 1;
-  return 256 + fwd_bounds_bytes((int)n_tasks) + (size_t)2 * (size_t)n_tasks * (size_t)N * sizeof(float);
+  return fwd_bounds_bytes((int)n_tasks) + (size_t)2 * (size_t)n_tasks * (size_t)N * sizeof(float);
 }
 
-int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, Boundary* out, cudaStream_t s) {
+int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s) {
   const int n = k.n_tasks + 1;
-  partition_kernel<<<(n + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, k.W, k.heavy, k.n_tasks, out);
+  B200_CUDA_OK(cudaMemsetAsync(part, 0, 16, s));  // fix_count
+  partition_kernel<<<(n + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, k.W, k.heavy, k.n_tasks, part);
   B200_LAUNCH_OK("partition_kernel");
   return B200_OK;
 }
 
-// workspace layout: [split flag, 256 B][boundaries (unless cached_bnd)][pieces 2 * n_tasks * N]
+// workspace layout: [partition block (unless cached)][pieces 2 * n_tasks * N]
 int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_bytes,
-                        const Boundary* cached_bnd, const FwdPick* cached_pick, cudaStream_t s) {
+                        const void* cached_part, const FwdPick* cached_pick, cudaStream_t s) {
   FwdParams p = pin;
   if (p.M == 0 || p.N == 0) return B200_OK;
   if (p.nnz == 0) {  // all rows empty: C = 0
@@ -576,13 +591,13 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
   const bool a4 = is_aligned(p.B, 16) && is_aligned(p.C, 16) && (p.ldb % 4 == 0) && (p.ldc % 4 == 0);
   const bool a2 = is_aligned(p.B, 8) && is_aligned(p.C, 8) && (p.ldb % 2 == 0) && (p.ldc % 2 == 0);
   FwdPick k = fwd_pick(p.M, p.nnz, p.N, a4, a2, -1);
-  const bool use_cache = cached_bnd != nullptr && cached_pick != nullptr && cached_pick->W == k.W &&
+  const bool use_cache = cached_part != nullptr && cached_pick != nullptr && cached_pick->W == k.W &&
                          cached_pick->heavy == k.heavy && cached_pick->n_tasks == k.n_tasks;
   if (use_cache) k.may_split = cached_pick->may_split;
-  const size_t bnd_bytes = use_cache ? 0 : fwd_bounds_bytes(k.n_tasks);
+  const size_t part_bytes = use_cache ? 0 : fwd_bounds_bytes(k.n_tasks);
   const size_t pieces_bytes = k.may_split ? (size_t)2 * (size_t)k.n_tasks * (size_t)p.N * sizeof(float) : 0;
-  const size_t need = 256 + bnd_bytes + pieces_bytes;
-  if (workspace == nullptr) {
+  const size_t need = part_bytes + pieces_bytes;
+  if (workspace == nullptr && need > 0) {
     void* w = nullptr;
     int rc = get_scratch(need, &w);
     if (rc != B200_OK) return rc;
@@ -593,24 +608,21 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
     set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
     return B200_ERR_INVALID;
   }
-  if (!is_aligned(workspace, 16)) {
+  if (need > 0 && !is_aligned(workspace, 16)) {
     set_error("workspace must be 16-byte aligned");
     return B200_ERR_INVALID;
   }
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-  p.split_flag = reinterpret_cast<int*>(ws);
-  const Boundary* bnd = cached_bnd;
+  const void* part = cached_part;
   if (!use_cache) {
-    Boundary* b = reinterpret_cast<Boundary*>(ws + 256);
-    int rc = launch_partition(p.row_ptr, p.M, p.nnz, k, b, s);
+    int rc = launch_partition(p.row_ptr, p.M, p.nnz, k, ws, s);
     if (rc != B200_OK) return rc;
-    bnd = b;
+    part = ws;
   }
-  p.pieces = reinterpret_cast<float*>(ws + 256 + bnd_bytes);
-  if (k.may_split) B200_CUDA_OK(cudaMemsetAsync(p.split_flag, 0, sizeof(int), s));
+  p.pieces = reinterpret_cast<float*>(ws + part_bytes);
   const int want_stage = (p.stage >= 0) ? p.stage : options().stage_mode;
   const bool stage = want_stage == 1 && is_aligned(p.col, 16) && is_aligned(p.val, 16);
-  return stage ? dispatch<true>(p, k, bnd, s) : dispatch<false>(p, k, bnd, s);
+  return stage ? dispatch<true>(p, k, part, s) : dispatch<false>(p, k, part, s);
 }
 
 }  // namespace b200
