@@ -101,6 +101,7 @@ struct b200_plan {
   FwdPick pick[2];
   bool bnd_valid[2] = {false, false};
   int t_max_row = -1;
+  Boundary* sd_bnd = nullptr;  // SDDMM task boundaries (heavy threshold 0)
 };
 
 // Boundaries depend on (row_ptr, W, heavy) only: compute once per plan side, reuse for every N.
@@ -266,7 +267,8 @@ int b200_sddmm_csr(const int32_t* d_row_ptr, const int32_t* d_col_ind, int64_t M
   if (nnz == 0) return B200_OK;
   B200_REQUIRE(d_row_ptr && d_col_ind && d_out_val, "null CSR / output pointer");
   B200_REQUIRE(N == 0 || (d_G && d_B), "null G / B");
-  return launch_sddmm(d_row_ptr, d_col_ind, (int)M, (int)nnz, d_G, ldg, d_B, ldb, (int)N, d_out_val,
+  B200_REQUIRE(ldg < 0x7fffffffLL && ldb < 0x7fffffffLL, "leading dimension out of range");
+  return launch_sddmm(d_row_ptr, d_col_ind, (int)M, (int)nnz, d_G, ldg, d_B, ldb, (int)N, d_out_val, nullptr,
                       (cudaStream_t)stream);
 }
 
@@ -378,7 +380,7 @@ int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const f
 int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
-  cudaFree(p->bnd[0]); cudaFree(p->bnd[1]);
+  cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd);
   cudaGetLastError();
   delete p;
   return B200_OK;
@@ -435,7 +437,17 @@ int b200_plan_backward_B(b200_plan* p, const float* d_G, int64_t ldg, int64_t N,
 int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,
                          int64_t N, float* d_dval, void* stream) {
   B200_REQUIRE(p != nullptr, "null plan");
-  return b200_sddmm_csr(p->row_ptr, p->col, p->M, p->K, p->nnz, d_G, ldg, d_B, ldb, N, d_dval, stream);
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  B200_REQUIRE(ldg >= N && ldb >= N && ldg < 0x7fffffffLL && ldb < 0x7fffffffLL, "bad leading dimension");
+  if (p->nnz == 0 || p->M == 0) return B200_OK;
+  B200_REQUIRE(d_dval != nullptr && (N == 0 || (d_G && d_B)), "null G / B / output");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->sd_bnd == nullptr) {
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->sd_bnd), sddmm_bounds_bytes(p->M, p->nnz)));
+    int rc = launch_sddmm_partition(p->row_ptr, p->M, p->nnz, p->sd_bnd, s);
+    if (rc) return rc;
+  }
+  return launch_sddmm(p->row_ptr, p->col, p->M, p->nnz, d_G, ldg, d_B, ldb, (int)N, d_dval, p->sd_bnd, s);
 }
 
 // ---- host-buffer entry points ------------------------------------------------------------

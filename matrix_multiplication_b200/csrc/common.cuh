@@ -203,8 +203,12 @@ int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void*
 // cached_bnd / cached_pick: boundaries a plan computed earlier for the same (W, heavy, n_tasks); may be null
 int launch_spmm_forward(const FwdParams& p, void* workspace, size_t workspace_bytes,
                         const void* cached_part, const FwdPick* cached_pick, cudaStream_t s);
+int sddmm_n_tasks(long long M, long long nnz);
+size_t sddmm_bounds_bytes(long long M, long long nnz);
+int launch_sddmm_partition(const int* row_ptr, int M, int nnz, Boundary* out, cudaStream_t s);
+// cached_bnd: boundaries from launch_sddmm_partition for the same row_ptr (a plan keeps them); may be null
 int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
-                 const float* B, long long ldb, int N, float* out, cudaStream_t s);
+                 const float* B, long long ldb, int N, float* out, const Boundary* cached_bnd, cudaStream_t s);
 int launch_transpose(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz,
                      int* t_row_ptr, int* t_col, float* t_val, int* t_perm, cudaStream_t s);
 int launch_gather(const float* src, const int* perm, long long n, float* dst, cudaStream_t s);
