@@ -151,6 +151,17 @@ int b200_plan_stats(const b200_plan* plan, int64_t* max_row_nnz, int64_t* empty_
 
 int b200_plan_forward(b200_plan* plan, const float* d_B, int64_t ldb, int64_t N,
                       float* d_C, int64_t ldc, void* stream);
+/* Multi-GPU forward (row-sharded A, one plan per rank; the reference is single-GPU, src/sparse_mm.cu:295):
+ * same as b200_plan_forward, and every finished row of C is ALSO stored into the same row block of the other
+ * ranks' buffers from the kernel's epilogue, so the all-gather of C overlaps the product instead of following it.
+ *   peer_C   : n_peers (<= 7) device pointers, mapped into this process (CUDA IPC / symmetric memory), each
+ *              pointing at THIS rank's row block inside a peer's C buffer (same ldc); may be NULL if n_peers == 0;
+ *   mc_C     : optional NVLS multicast address of this rank's row block (multimem.st: the NVSwitch replicates the
+ *              store to every rank, this one included); when non-NULL it replaces d_C and peer_C as the target.
+ * The caller synchronises the ranks afterwards (a barrier) before anyone reads a peer-written row.  N >= 24. */
+int b200_plan_forward_peers(b200_plan* plan, const float* d_B, int64_t ldb, int64_t N,
+                            float* d_C, int64_t ldc, float* const* peer_C, int n_peers, float* mc_C,
+                            void* stream);
 /* grad_B[K,N] = A^T * G[M,N]  — SpMM over the cached transposed CSR (matmuls.py:253). */
 int b200_plan_backward_B(b200_plan* plan, const float* d_G, int64_t ldg, int64_t N,
                          float* d_dB, int64_t lddb, void* stream);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "b200_plan_values_updated": (C.c_int, [_vp]),
     "b200_plan_stats": (C.c_int, [_vp, _i64p, _i64p]),
     "b200_plan_forward": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "b200_plan_forward_peers": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), C.c_int, _vp, _vp]),
     "b200_plan_backward_B": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b200_plan_backward_A": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
     "b200_spmm_csr_forward_host": (C.c_int, [_i32p, _i32p, _f32p, _i64, _i64, _i64, _f32p, _i64, _f32p]),
@@ -260,6 +261,15 @@ class Plan:
     def forward(self, B, Cout, stream=0):
         N = B.shape[1]
         check(lib().b200_plan_forward(self._h, _dp(B), N, N, _dp(Cout), N, C.c_void_p(stream)))
+        return Cout
+
+    def forward_peers(self, B, Cout, peer_ptrs=(), mc_ptr=0, stream=0):
+        """Forward whose epilogue also stores every row into peers' buffers (raw device addresses of THIS
+        rank's row block inside each peer's C) or to an NVLS multicast address (mc_ptr)."""
+        N = B.shape[1]
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(x)) for x in peer_ptrs])
+        check(lib().b200_plan_forward_peers(self._h, _dp(B), N, N, _dp(Cout), N, arr, len(peer_ptrs),
+                                            C.c_void_p(int(mc_ptr)) if mc_ptr else None, C.c_void_p(stream)))
         return Cout
 
     def backward_B(self, G, dB, stream=0):

@@ -401,7 +401,7 @@ int b200_plan_stats(const b200_plan* p, int64_t* max_row_nnz, int64_t* empty_row
 
 static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M,
                      int K, int max_row, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
-                     cudaStream_t s) {
+                     cudaStream_t s, float* const* peer_C = nullptr, int n_peers = 0, float* mc_C = nullptr) {
   B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
   B200_REQUIRE(ldb >= N && ldc >= N, "leading dimension smaller than N");
   B200_REQUIRE(ldb < 0x7fffffffLL && ldc < 0x7fffffffLL, "leading dimension out of range");
@@ -414,6 +414,9 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
   FwdParams q{};
   q.row_ptr = row_ptr; q.col = col; q.val = val; q.M = M; q.nnz = p->nnz;
   q.B = d_B; q.ldb = ldb; q.N = (int)N; q.C = d_C; q.ldc = ldc; q.stage = -1;
+  for (int i = 0; i < n_peers; ++i) q.peer[i] = peer_C[i];
+  q.n_peers = n_peers;
+  q.mc = mc_C;
   return launch_spmm_forward(q, p->ws, p->ws_bytes, p->bnd_valid[side] ? p->bnd[side] : nullptr,
                              p->bnd_valid[side] ? &p->pick[side] : nullptr, s);
 }
@@ -423,6 +426,16 @@ int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, fl
   B200_REQUIRE(p != nullptr, "null plan");
   return plan_spmm(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc,
                    (cudaStream_t)stream);
+}
+
+int b200_plan_forward_peers(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
+                            float* const* peer_C, int n_peers, float* mc_C, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  B200_REQUIRE(n_peers >= 0 && n_peers <= 7, "n_peers must be in [0, 7]");
+  B200_REQUIRE(n_peers == 0 || peer_C != nullptr, "null peer pointer array");
+  for (int i = 0; i < n_peers; ++i) B200_REQUIRE(peer_C[i] != nullptr, "null peer pointer");
+  return plan_spmm(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc,
+                   (cudaStream_t)stream, peer_C, n_peers, mc_C);
 }
 
 int b200_plan_backward_B(b200_plan* p, const float* d_G, int64_t ldg, int64_t N, float* d_dB,

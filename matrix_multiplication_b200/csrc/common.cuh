@@ -136,6 +136,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
       : "memory");
 }
 
+// multimem.st: one store to a multicast address, replicated by the switch (NVLS)
+__device__ __forceinline__ void multimem_st(float* p, float a, float b, float c, float d) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b),
+               "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st(float* p, float a, float b) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void multimem_st(float* p, float a) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
 // read-only 128/64/32-bit loads of B (gathered rows; keep in L1/L2)
 template <int VEC>
 struct Vec;
@@ -152,6 +165,7 @@ struct Vec<4> {
   __device__ __forceinline__ void store(float* p) const {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  __device__ __forceinline__ void store_mc(float* p) const { multimem_st(p, v[0], v[1], v[2], v[3]); }
 };
 template <>
 struct Vec<2> {
@@ -166,6 +180,7 @@ struct Vec<2> {
   __device__ __forceinline__ void store(float* p) const {
     *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
   }
+  __device__ __forceinline__ void store_mc(float* p) const { multimem_st(p, v[0], v[1]); }
 };
 template <>
 struct Vec<1> {
@@ -173,6 +188,7 @@ struct Vec<1> {
   __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
   __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, v[0]); }
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+  __device__ __forceinline__ void store_mc(float* p) const { multimem_st(p, v[0]); }
 };
 #endif  // __CUDACC__
 
@@ -190,6 +206,12 @@ struct FwdParams {
   long long ldc;
   float* pieces;   // workspace: [2 * n_tasks][N] partial rows of split heavy rows
   int stage;       // 1 / 0 force TMA staging on / off, -1 = process option
+  // multi-GPU epilogue (row-sharded A): every finished row of C is also stored into the same row block of
+  // the other ranks' buffers — plain P2P stores to mapped peer pointers, or one multimem.st to an NVLS
+  // multicast address that the NVSwitch replicates to every rank (including this one).
+  float* peer[7];
+  int n_peers;
+  float* mc;
 };
 // lane layout + task size chosen for a problem (spmm_fwd.cu)
 struct FwdPick {

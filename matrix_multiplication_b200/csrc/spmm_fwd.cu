@@ -60,6 +60,17 @@ partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int hea
   }
 }
 
+// A finished row slab of C: local store, plus the multi-GPU epilogue (peer stores / multicast store).
+template <int VEC>
+__device__ __forceinline__ void store_c(const FwdParams& p, long long off, const Vec<VEC>& o) {
+  if (p.mc != nullptr) {
+    o.store_mc(p.mc + off);  // the switch delivers it to every rank, this one included
+    return;
+  }
+  o.store_stream(p.C + off);
+  for (int q = 0; q < p.n_peers; ++q) o.store_stream(p.peer[q] + off);
+}
+
 template <int VEC, int LPR, int U, bool STAGE>
 __global__ void __launch_bounds__(WARPS * 32)
 spmm_fwd_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, int n_tasks) {
@@ -294,7 +305,7 @@ spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, i
           Vec<VEC> z;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) z.v[v] = 0.f;
-          z.store_stream(p.C + (long long)(base + b) * p.ldc + col0);
+          store_c<VEC>(p, (long long)(base + b) * p.ldc + col0, z);
         }
       }
     }
@@ -316,19 +327,17 @@ spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, i
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
   auto emit = [&](int off) {  // the non-zero at staged offset `off` is the last one of its row
-    float* dst;
-    if (head) {
-      dst = p.pieces + (size_t)(2 * (size_t)t) * p.N + col0;
-      head = false;
-    } else {
-      dst = p.C + (long long)s_rowend[off] * p.ldc + col0;
-    }
     if (active) {
       Vec<VEC> o;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
-      o.store_stream(dst);
+      if (head) {
+        o.store_stream(p.pieces + (size_t)(2 * (size_t)t) * p.N + col0);
+      } else {
+        store_c<VEC>(p, (long long)s_rowend[off] * p.ldc + col0, o);
+      }
     }
+    head = false;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   };
@@ -438,7 +447,7 @@ spmm_fixup_kernel(FwdParams p, const void* __restrict__ part, int W, int n_tasks
 #pragma unroll
       for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
     }
-    sum.store_stream(p.C + (long long)i * p.ldc + col0);
+    store_c<VEC>(p, (long long)i * p.ldc + col0, sum);
   }
 }
 
@@ -508,6 +517,10 @@ int launch_flat_nb(const FwdParams& p, const FwdPick& k, const void* bnd, cudaSt
 
 template <bool STAGE>
 int dispatch(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
+  if (k.lpr != 32 && (p.n_peers > 0 || p.mc != nullptr)) {
+    set_error("the multi-GPU epilogue needs N >= 24 dense columns");
+    return B200_ERR_INVALID;
+  }
   if (k.lpr == 32) {
     if (k.vec == 4) return launch_flat_nb<4, STAGE>(p, k, bnd, s);
     if (k.vec == 2) return launch_flat_nb<2, STAGE>(p, k, bnd, s);

@@ -59,3 +59,40 @@ class RowGather:
         for wk in works:
             wk.wait()
         return self.buffer
+
+
+class SymmetricRowGather:
+    '''The all-gather of C fused into the SpMM epilogue: C lives in a symmetric-memory buffer (same
+    allocation on every rank, every rank's copy mapped into every process over NVLink), and the forward
+    kernel stores each finished row into all copies at once — P2P stores to the mapped peer pointers, or a
+    single ``multimem.st`` to the NVLS multicast address when the fabric supports it.  After the kernel a
+    device-side barrier on the signal pads makes the rows visible everywhere; no NCCL collective follows.
+
+    torch.distributed._symmetric_memory is used for the plumbing only (allocation, handle exchange, barrier).'''
+
+    def __init__(self, bounds, N: int, device, dist, use_multicast: bool = True):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.bounds = [int(b) for b in bounds]
+        self.dist = dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        M = self.bounds[-1]
+        self.buffer = symm_mem.empty(M, N, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, dist.group.WORLD)
+        r0 = self.bounds[self.rank]
+        off = r0 * N * 4
+        self.local = self.buffer[r0:self.bounds[self.rank + 1]]
+        ptrs = list(self.handle.buffer_ptrs)
+        self.peer_ptrs = [int(ptrs[q]) + off for q in range(self.world) if q != self.rank]
+        mc = int(self.handle.multicast_ptr or 0) if use_multicast else 0  # 0: no NVLS multicast on this fabric
+        self.mc_ptr = (mc + off) if mc else 0
+
+    def forward(self, plan, B, stream=0):
+        '''Rank-local SpMM whose epilogue writes this rank's rows of C into every rank's buffer.'''
+        if self.mc_ptr:
+            plan.forward_peers(B, self.local, (), self.mc_ptr, stream=stream)
+        else:
+            plan.forward_peers(B, self.local, self.peer_ptrs, 0, stream=stream)
+
+    def barrier(self):
+        self.handle.barrier(channel=0)

@@ -286,3 +286,25 @@ def test_full_size_rmat_properties():
     ref = oracle.spmm_f64(sub_rp, ci[idx], va[idx], (len(rows), K), B1.cpu().numpy())
     assert oracle.rel_err(Ca[torch.from_numpy(rows).to(dev)].cpu().numpy(), ref) <= TOL
     plan.close()
+
+
+def test_peer_store_epilogue_on_one_gpu():
+    """The multi-GPU epilogue with two stand-in 'peers' (extra buffers on the same GPU): every row —
+    light, heavy (fix-up path) and empty (zero fill) — must land identically in all three copies."""
+    import torch
+    rng = np.random.default_rng(31)
+    M, K, N = 700, 3000, 128
+    rp, ci, va, _ = random_csr(rng, M, K, 0.01, heavy_rows=(5, 300), empty_rows=(0, 6, 699))
+    dev = torch.device("cuda:0")
+    crow, col, val = (torch.from_numpy(x).to(dev) for x in (rp, ci, va))
+    B = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(dev)
+    plan = capi.Plan(crow, col, val, (M, K))
+    C0 = torch.full((M, N), 7.0, device=dev)
+    P1 = torch.full((M, N), 8.0, device=dev)
+    P2 = torch.full((M, N), 9.0, device=dev)
+    plan.forward_peers(B, C0, [P1.data_ptr(), P2.data_ptr()])
+    torch.cuda.synchronize()
+    ref = oracle.spmm_f64(rp, ci, va, (M, K), B.cpu().numpy())
+    assert oracle.rel_err(C0.cpu().numpy(), ref) <= TOL
+    assert torch.equal(C0, P1) and torch.equal(C0, P2)
+    plan.close()
