@@ -72,8 +72,11 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "configs.json"))
     ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    for o in args.opt:
+        capi.set_option(o.split("=")[0], int(o.split("=")[1]))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush = lambda: flush_buf.fill_(1)  # noqa: E731
     ref_cm = None

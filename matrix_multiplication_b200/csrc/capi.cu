@@ -212,6 +212,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
   if (!strcmp(name, "batch")) { options().batch = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
+  if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
   return B200_ERR_INVALID;
 }
@@ -221,6 +222,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "batch")) return options().batch;
   if (!strcmp(name, "pipeline")) return options().pipeline;
+  if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
   return -1;
 }
 

@@ -184,6 +184,83 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
   }
 }
 
+// ---- small N (< 24): G = 32 / LPR lane groups, each walking its own merge-path task, LPR lanes across the
+// dense dimension; boundaries are searched in the kernel (tasks are tiny, no staging).
+constexpr int SDS_WARPS = 8;
+
+template <int LPR, int VEC>
+__global__ void __launch_bounds__(SDS_WARPS * 32)
+sddmm_grouped_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int nnz,
+             const float* __restrict__ G, long long ldg, const float* __restrict__ B,
+             long long ldb, int N, float* __restrict__ out, int W, int n_tasks) {
+  constexpr int GROUPS = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / LPR, gl = lane % LPR;
+  long long t = ((long long)blockIdx.x * SDS_WARPS + warp) * GROUPS + grp;
+  if (t > n_tasks) t = n_tasks;
+  long long t1 = t + 1;
+  if (t1 > n_tasks) t1 = n_tasks;
+  const Boundary b0 = merge_path_boundary(row_ptr, M, nnz, t * (long long)W, 0);
+  const Boundary b1 = merge_path_boundary(row_ptr, M, nnz, t1 * (long long)W, 0);
+  const int j0 = b0.nz, j1 = b1.nz;
+  int row = b0.row;
+  int row_end = (row < M) ? __ldg(row_ptr + row + 1) : 0x7fffffff;
+  const int slab_w = LPR * VEC;
+  const int slabs = (N + slab_w - 1) / slab_w;
+
+  int n_iter = (j1 - j0 + LPR - 1) / LPR;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) n_iter = max(n_iter, __shfl_xor_sync(FULL, n_iter, o));
+
+  for (int it = 0; it < n_iter; ++it) {
+    const int chunk = j0 + it * LPR;
+    const int idx = chunk + gl;
+    const int creg = (idx < j1) ? __ldg(col + idx) : 0;
+#pragma unroll 4
+    for (int k = 0; k < LPR; ++k) {
+      const int pp = chunk + k;
+      const int c = __shfl_sync(FULL, creg, k, LPR);
+      const bool valid = pp < j1;
+      float part = 0.f;
+      if (valid) {
+        while (pp >= row_end) {
+          ++row;
+          row_end = __ldg(row_ptr + row + 1);
+        }
+        const float* g = G + (long long)row * ldg + gl * VEC;
+        const float* b = B + (long long)c * ldb + gl * VEC;
+        for (int s = 0; s < slabs; ++s) {
+          if (s * slab_w + gl * VEC < N) {
+            Vec<VEC> gv, bv;
+            gv.load(g + s * slab_w);
+            bv.load(b + s * slab_w);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) part = fmaf(gv.v[v], bv.v[v], part);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o >= 1; o >>= 1) part += __shfl_xor_sync(FULL, part, o, LPR);
+      if (valid && gl == 0) out[pp] = part;
+    }
+  }
+}
+
+template <int LPR, int VEC>
+int launch_grouped(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
+               const float* B, long long ldb, int N, float* out, cudaStream_t s) {
+  constexpr int GROUPS = 32 / LPR;
+  const int W = 256;
+  const long long items = (long long)M + nnz;
+  const int n_tasks = (int)((items + W - 1) / W);
+  const int per_cta = SDS_WARPS * GROUPS;
+  dim3 grid((unsigned)((n_tasks + per_cta - 1) / per_cta));
+  sddmm_grouped_kernel<LPR, VEC><<<grid, SDS_WARPS * 32, 0, s>>>(row_ptr, col, M, nnz, G, ldg, B, ldb, N,
+                                                       out, W, n_tasks);
+  B200_LAUNCH_OK("sddmm_kernel");
+  return B200_OK;
+}
+
 inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 template <int VEC, bool TMA>
@@ -224,6 +301,23 @@ int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float
     B200_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)nnz * sizeof(float), s));
     return B200_OK;
   }
+  const bool a4 = N % 4 == 0 && is_aligned(G, 16) && is_aligned(B, 16) && ldg % 4 == 0 && ldb % 4 == 0;
+  const bool a2 = N % 2 == 0 && is_aligned(G, 8) && is_aligned(B, 8) && ldg % 2 == 0 && ldb % 2 == 0;
+  if (N < 24) {  // lane groups: 32 / LPR non-zeros per gather instruction
+    if (a4) {
+      if (N <= 16) return launch_grouped<4, 4>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+      return launch_grouped<8, 4>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+    }
+    if (a2) {
+      if (N <= 8) return launch_grouped<4, 2>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+      if (N <= 16) return launch_grouped<8, 2>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+      return launch_grouped<16, 2>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+    }
+    if (N <= 4) return launch_grouped<4, 1>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+    if (N <= 8) return launch_grouped<8, 1>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+    if (N <= 16) return launch_grouped<16, 1>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+    return launch_grouped<32, 1>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, s);
+  }
   const Boundary* bnd = cached_bnd;
   if (bnd == nullptr) {
     void* w = nullptr;
@@ -234,8 +328,6 @@ int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float
     bnd = reinterpret_cast<const Boundary*>(w);
   }
   const int n_tasks = sddmm_n_tasks(M, nnz);
-  const bool a4 = N % 4 == 0 && is_aligned(G, 16) && is_aligned(B, 16) && ldg % 4 == 0 && ldb % 4 == 0;
-  const bool a2 = N % 2 == 0 && is_aligned(G, 8) && is_aligned(B, 8) && ldg % 2 == 0 && ldb % 2 == 0;
   const int vmax = a4 ? 4 : (a2 ? 2 : 1);
   int vec = 1;
   while (vec < vmax && 32 * vec < N) vec <<= 1;

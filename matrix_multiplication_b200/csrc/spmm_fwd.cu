@@ -543,7 +543,7 @@ int dispatch(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t
 FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2, int max_row) {
   FwdPick k;
   const int vmax = (N % 4 == 0 && aligned4) ? 4 : ((N % 2 == 0 && aligned2) ? 2 : 1);
-  if (N >= 24) {
+  if (N >= options().flat_min_n) {
     // one lane group of 32 lanes (flat kernel): the narrowest vector that covers N in one slab
     k.vec = 1;
     while (k.vec < vmax && 32LL * k.vec < N) k.vec <<= 1;
