@@ -20,7 +20,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SD_NW = 4;    // warps (= tasks) per CTA
-constexpr int SD_W = 256;   // items per task
+constexpr int SD_W = 256;   // items per task (smaller for small problems, see sd_items)
 
 __host__ __device__ inline int sd_capacity(int W) { return ((SD_NW * W + 24) + 7) & ~7; }
 
@@ -184,6 +184,8 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
   }
 }
 
+int sd_items(long long M, long long nnz);
+
 // ---- small N (< 24): G = 32 / LPR lane groups, each walking its own merge-path task, LPR lanes across the
 // dense dimension; boundaries are searched in the kernel (tasks are tiny, no staging).
 constexpr int SDS_WARPS = 8;
@@ -250,14 +252,14 @@ template <int LPR, int VEC>
 int launch_grouped(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
                const float* B, long long ldb, int N, float* out, cudaStream_t s) {
   constexpr int GROUPS = 32 / LPR;
-  const int W = 256;
+  const int W = std::max(32, sd_items(M, nnz) / 2);  // a lane group, not a warp, walks a task here
   const long long items = (long long)M + nnz;
   const int n_tasks = (int)((items + W - 1) / W);
   const int per_cta = SDS_WARPS * GROUPS;
   dim3 grid((unsigned)((n_tasks + per_cta - 1) / per_cta));
   sddmm_grouped_kernel<LPR, VEC><<<grid, SDS_WARPS * 32, 0, s>>>(row_ptr, col, M, nnz, G, ldg, B, ldb, N,
                                                        out, W, n_tasks);
-  B200_LAUNCH_OK("sddmm_kernel");
+  B200_LAUNCH_OK("sddmm_grouped_kernel");
   return B200_OK;
 }
 
@@ -267,20 +269,29 @@ template <int VEC, bool TMA>
 int launch_one(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
                const float* B, long long ldb, int N, float* out, const Boundary* bnd, int n_tasks,
                cudaStream_t s) {
-  const int cap = sd_capacity(SD_W);
+  const int W = sd_items(M, nnz);
+  const int cap = sd_capacity(W);
   constexpr int BND_BYTES = ((SD_NW + 1) * (int)sizeof(Boundary) + 15) & ~15;
   const size_t smem = 16 + BND_BYTES + (size_t)cap * 8;
   dim3 grid((unsigned)((n_tasks + SD_NW - 1) / SD_NW));
   sddmm_kernel<VEC, TMA><<<grid, SD_NW * 32, smem, s>>>(row_ptr, col, M, nnz, G, (unsigned)ldg, B,
-                                                         (unsigned)ldb, N, out, bnd, SD_W, n_tasks);
+                                                         (unsigned)ldb, N, out, bnd, W, n_tasks);
   B200_LAUNCH_OK("sddmm_kernel");
   return B200_OK;
 }
 
 }  // namespace
 
+namespace {
+int sd_items(long long M, long long nnz) {  // same rule as the forward: spread small problems over the SMs
+  const long long spread = (M + nnz) / (148 * 8);
+  const int W = (int)std::min<long long>(SD_W, std::max<long long>(32, spread));
+  return (W + 31) & ~31;
+}
+}  // namespace
 int sddmm_n_tasks(long long M, long long nnz) {
-  const long long n = (M + nnz + SD_W - 1) / SD_W;
+  const int W = sd_items(M, nnz);
+  const long long n = (M + nnz + W - 1) / W;
   return (int)(n < 1 ? 1 : n);
 }
 size_t sddmm_bounds_bytes(long long M, long long nnz) {
@@ -288,7 +299,7 @@ size_t sddmm_bounds_bytes(long long M, long long nnz) {
 }
 int launch_sddmm_partition(const int* row_ptr, int M, int nnz, Boundary* out, cudaStream_t s) {
   const int n_tasks = sddmm_n_tasks(M, nnz);
-  sddmm_partition_kernel<<<(n_tasks + 1 + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, SD_W, n_tasks, out);
+  sddmm_partition_kernel<<<(n_tasks + 1 + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, sd_items(M, nnz), n_tasks, out);
   B200_LAUNCH_OK("sddmm_partition_kernel");
   return B200_OK;
 }

@@ -554,7 +554,12 @@ FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool al
     while (k.lpr < 16 && (long long)k.lpr * k.vec < N) k.lpr <<= 1;
   }
   int W = options().items_per_task;
-  if (W <= 0) W = 256;
+  if (W <= 0) {
+    // 256 items per warp task; small problems get smaller tasks so that they still spread over the
+    // 148 SMs (a task is a serial chain of 8-wide gather batches: ~1 us per batch)
+    const long long spread = (M + nnz) / (148 * 8);
+    W = (int)std::min<long long>(256, std::max<long long>(32, spread));
+  }
   W = (W + 31) & ~31;
   if (W > 2048) W = 2048;
   while (W > 128 && (size_t)smem_capacity(W, W) * 12 > 160 * 1024) W >>= 1;
@@ -573,13 +578,9 @@ size_t fwd_bounds_bytes(int n_tasks) {
 }
 
 size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
-  // sized for the smallest task size the launcher may pick; keep in sync with fwd_pick().
-  int W = options().items_per_task;
-  if (W <= 0 || W > 128) W = 128;
-  W = (W + 31) & ~31;
-  long long n_tasks = (M + nnz + W - 1) / W;
-  if (n_tasks < 1) n_tasks = 1;
-  return fwd_bounds_bytes((int)n_tasks) + (size_t)2 * (size_t)n_tasks * (size_t)N * sizeof(float);
+  // the task size depends on (M, nnz) and the items_per_task option only, not on N or alignment
+  const FwdPick k = fwd_pick(M, nnz, N > 0 ? N : 1, true, true, -1);
+  return fwd_bounds_bytes(k.n_tasks) + (size_t)2 * (size_t)k.n_tasks * (size_t)N * sizeof(float);
 }
 
 int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s) {

@@ -123,6 +123,7 @@ def test_forward_matches_csr_order_fp32_when_rows_are_not_split():
     rng = np.random.default_rng(12)
     rp, ci, va, _ = random_csr(rng, 300, 400, 0.05)
     B = rng.standard_normal((400, 128)).astype(np.float32)  # N >= 128: one lane group per row
+    capi.set_option("items_per_task", 256)  # no row is longer than a task: nothing is split
     C = capi.spmm_host(rp, ci, va, (300, 400), B)
     np.testing.assert_array_equal(bits(C), bits(oracle.spmm_f32(rp, ci, va, (300, 400), B, fused=True)))
 
