@@ -416,11 +416,13 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
   FwdParams q{};
   q.row_ptr = row_ptr; q.col = col; q.val = val; q.M = M; q.nnz = p->nnz;
   q.B = d_B; q.ldb = ldb; q.N = (int)N; q.C = d_C; q.ldc = ldc; q.stage = -1;
-  for (int i = 0; i < n_peers; ++i) q.peer[i] = peer_C[i];
-  q.n_peers = n_peers;
-  q.mc = mc_C;
+  PeerSet ps{};
+  for (int i = 0; i < n_peers; ++i) ps.peer[i] = peer_C[i];
+  ps.n_peers = n_peers;
+  ps.mc = mc_C;
   return launch_spmm_forward(q, p->ws, p->ws_bytes, p->bnd_valid[side] ? p->bnd[side] : nullptr,
-                             p->bnd_valid[side] ? &p->pick[side] : nullptr, s);
+                             p->bnd_valid[side] ? &p->pick[side] : nullptr, s,
+                             (n_peers > 0 || mc_C != nullptr) ? &ps : nullptr);
 }
 
 int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,

@@ -207,12 +207,25 @@ struct FwdParams {
   long long ldc;
   float* pieces;   // workspace: [2 * n_tasks][N] partial rows of split heavy rows
   int stage;       // 1 / 0 force TMA staging on / off, -1 = process option
-  // multi-GPU epilogue (row-sharded A): every finished row of C is also stored into the same row block of
-  // the other ranks' buffers — plain P2P stores to mapped peer pointers, or one multimem.st to an NVLS
-  // multicast address that the NVSwitch replicates to every rank (including this one).
+};
+// multi-GPU epilogue (row-sharded A): every finished row of C is also stored into the same row block of
+// the other ranks' buffers — plain P2P stores to mapped peer pointers, or one multimem.st to an NVLS
+// multicast address that the NVSwitch replicates to every rank (including this one).  Kept out of
+// FwdParams so that the single-GPU kernels carry none of it.
+struct PeerSet {
   float* peer[7];
   int n_peers;
   float* mc;
+};
+template <bool PEERS>
+struct PeerArg;
+template <>
+struct PeerArg<true> {
+  PeerSet s;
+};
+template <>
+struct PeerArg<false> {
+  char unused;
 };
 // lane layout + task size chosen for a problem (spmm_fwd.cu)
 struct FwdPick {
@@ -225,7 +238,8 @@ size_t fwd_bounds_bytes(int n_tasks);
 int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s);
 // cached_bnd / cached_pick: boundaries a plan computed earlier for the same (W, heavy, n_tasks); may be null
 int launch_spmm_forward(const FwdParams& p, void* workspace, size_t workspace_bytes,
-                        const void* cached_part, const FwdPick* cached_pick, cudaStream_t s);
+                        const void* cached_part, const FwdPick* cached_pick, cudaStream_t s,
+                        const PeerSet* peers = nullptr);
 int sddmm_n_tasks(long long M, long long nnz);
 size_t sddmm_bounds_bytes(long long M, long long nnz);
 int launch_sddmm_partition(const int* row_ptr, int M, int nnz, Boundary* out, cudaStream_t s);

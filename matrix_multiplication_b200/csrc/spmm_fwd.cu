@@ -61,14 +61,20 @@ partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int hea
 }
 
 // A finished row slab of C: local store, plus the multi-GPU epilogue (peer stores / multicast store).
-template <int VEC>
-__device__ __forceinline__ void store_c(const FwdParams& p, long long off, const Vec<VEC>& o) {
-  if (p.mc != nullptr) {
-    o.store_mc(p.mc + off);  // the switch delivers it to every rank, this one included
-    return;
+template <int VEC, bool PEERS>
+__device__ __forceinline__ void store_c(float* C, const PeerArg<PEERS>& ps, long long off, const Vec<VEC>& o) {
+  if constexpr (!PEERS) {
+    o.store_stream(C + off);
+  } else {
+    if (ps.s.mc != nullptr) {
+      o.store_mc(ps.s.mc + off);  // the switch delivers it to every rank, this one included
+      return;
+    }
+    o.store_stream(C + off);
+#pragma unroll
+    for (int q = 0; q < 7; ++q)  // static indices: the pointers stay in the constant bank
+      if (q < ps.s.n_peers) o.store_stream(ps.s.peer[q] + off);
   }
-  o.store_stream(p.C + off);
-  for (int q = 0; q < p.n_peers; ++q) o.store_stream(p.peer[q] + off);
 }
 
 template <int VEC, int LPR, int U, bool STAGE>
@@ -238,9 +244,9 @@ spmm_fwd_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, in
 // FMAs per lane.  Row ends are a per-chunk bit mask (built once per CTA from row_ptr, together with
 // the row id stored at each row-end position), so the common chunk without a row end runs
 // straight-line code and a row end costs one store.  Empty rows are zero-filled by the CTA up front.
-template <int VEC, bool TMA, int NB, int NW, int MINB>
+template <int VEC, bool TMA, int NB, int NW, int MINB, bool PEERS>
 __global__ void __launch_bounds__(NW * 32, MINB)
-spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, int n_tasks) {
+spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, int W, int heavy, int n_tasks) {
   const Boundary* bnd = part_bnd(part);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [mbar 16B][Boundary x (WARPS+1), 80B][mask words CAP/8 + 4][s_col CAP][s_val CAP][s_rowend CAP]
@@ -305,7 +311,7 @@ spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, i
           Vec<VEC> z;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) z.v[v] = 0.f;
-          store_c<VEC>(p, (long long)(base + b) * p.ldc + col0, z);
+          store_c<VEC, PEERS>(p.C, ps, (long long)(base + b) * p.ldc + col0, z);
         }
       }
     }
@@ -327,14 +333,20 @@ spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, i
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
   auto emit = [&](int off) {  // the non-zero at staged offset `off` is the last one of its row
+    float* dst;
+    if (head) {
+      dst = p.pieces + (size_t)(2 * (size_t)t) * p.N + col0;
+    } else {
+      dst = p.C + (long long)s_rowend[off] * p.ldc + col0;
+    }
     if (active) {
       Vec<VEC> o;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
-      if (head) {
-        o.store_stream(p.pieces + (size_t)(2 * (size_t)t) * p.N + col0);
+      if (PEERS && !head) {
+        store_c<VEC, PEERS>(p.C, ps, dst - p.C, o);
       } else {
-        store_c<VEC>(p, (long long)s_rowend[off] * p.ldc + col0, o);
+        o.store_stream(dst);
       }
     }
     head = false;
@@ -425,29 +437,50 @@ spmm_flat_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, i
   }
 }
 
-// Adds up the pieces of every split row in task order and writes the row of C.  One warp per
-// (fix-list entry, slab of 32 * VEC columns); exits at once when no row was split.
-template <int VEC>
+// Adds up the pieces of every split row and writes the row of C.  One CTA per (fix-list entry, slab of
+// 32 * VEC columns): warp w sums pieces w, w + 8, ... (a row of the R-MAT matrix has up to ~150), the 8
+// partial sums meet in shared memory and are added in warp order — a fixed tree, so results are
+// deterministic.  Exits at once when no row was split.
+template <int VEC, bool PEERS>
 __global__ void __launch_bounds__(256)
-spmm_fixup_kernel(FwdParams p, const void* __restrict__ part, int W, int n_tasks) {
+spmm_fixup_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, int W, int n_tasks) {
+  __shared__ float s_part[8][32 * VEC];
   const int count = *reinterpret_cast<const int*>(part);
   const Boundary* bnd = part_bnd(part);
   const int* list = part_fix_list(part, n_tasks);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col0 = blockIdx.y * (32 * VEC) + lane * VEC;
-  if (col0 >= p.N) return;
-  for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < count; e += gridDim.x * 8) {
+  const bool active = col0 < p.N;
+  for (int e = blockIdx.x; e < count; e += gridDim.x) {
     const int b = __ldg(list + e);
     const int i = bnd[b].row;
     const long long t_first = ((long long)__ldg(p.row_ptr + i) + i) / W;
-    Vec<VEC> sum, x;
-    sum.load(p.pieces + (size_t)(2 * t_first + 1) * p.N + col0);
-    for (long long t = t_first + 1; t <= b; ++t) {
-      x.load(p.pieces + (size_t)(2 * t) * p.N + col0);
+    // piece k of the row: k = 0 is the tail piece of task t_first, k >= 1 the head piece of task t_first + k
+    const int n_pieces = (int)(b - t_first) + 1;
+    Vec<VEC> sum;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
+    for (int v = 0; v < VEC; ++v) sum.v[v] = 0.f;
+    if (active) {
+      for (int k = warp; k < n_pieces; k += 8) {
+        Vec<VEC> x;
+        x.load(p.pieces + (size_t)(2 * (t_first + k) + (k == 0 ? 1 : 0)) * p.N + col0);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
+      }
     }
-    store_c<VEC>(p, (long long)i * p.ldc + col0, sum);
+    if (n_pieces > 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s_part[warp][lane * VEC + v] = sum.v[v];
+      __syncthreads();
+      if (warp == 0 && active) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) sum.v[v] += s_part[w][lane * VEC + v];
+      }
+      __syncthreads();
+    }
+    if (warp == 0 && active) store_c<VEC, PEERS>(p.C, ps, (long long)i * p.ldc + col0, sum);
   }
 }
 
@@ -462,17 +495,18 @@ __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
 inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 template <int VEC>
-int launch_fixup(const FwdParams& p, const FwdPick& k, const void* part, cudaStream_t s) {
+int launch_fixup(const FwdParams& p, const FwdPick& k, const void* part, cudaStream_t s, const PeerSet* peers) {
   if (k.n_tasks <= 1 || !k.may_split) return B200_OK;
   const int slabs = (p.N + 32 * VEC - 1) / (32 * VEC);
-  dim3 fgrid((unsigned)std::min(148 * 2, (k.n_tasks + 7) / 8), (unsigned)slabs);
-  spmm_fixup_kernel<VEC><<<fgrid, 256, 0, s>>>(p, part, k.W, k.n_tasks);
+  dim3 fgrid((unsigned)std::min(148 * 8, k.n_tasks), (unsigned)slabs);
+  if (peers != nullptr) spmm_fixup_kernel<VEC, true><<<fgrid, 256, 0, s>>>(p, PeerArg<true>{*peers}, part, k.W, k.n_tasks);
+  else spmm_fixup_kernel<VEC, false><<<fgrid, 256, 0, s>>>(p, PeerArg<false>{0}, part, k.W, k.n_tasks);
   B200_LAUNCH_OK("spmm_fixup_kernel");
   return B200_OK;
 }
 
 template <int VEC, int LPR, bool STAGE>
-int launch_one(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
+int launch_one(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s, const PeerSet* peers) {
   constexpr int U = (32 / LPR >= 4) ? 4 : 8;
   const int cap = smem_capacity(k.W, k.heavy);
   constexpr int BND_BYTES = ((WARPS + 1) * (int)sizeof(Boundary) + 15) & ~15;
@@ -484,50 +518,53 @@ int launch_one(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream
   dim3 grid((unsigned)((k.n_tasks + WARPS - 1) / WARPS), (unsigned)k.slabs);
   kern<<<grid, WARPS * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_fwd_kernel");
-  return launch_fixup<VEC>(p, k, bnd, s);
+  return launch_fixup<VEC>(p, k, bnd, s, peers);
 }
 
-template <int VEC, bool TMA, int NB, int NW, int MINB>
-int launch_flat(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
+template <int VEC, bool TMA, int NB, int NW, int MINB, bool PEERS>
+int launch_flat(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s, const PeerSet* peers) {
   const int cap = smem_capacity(k.W, k.heavy, NW);
   constexpr int BND_BYTES = ((NW + 1) * (int)sizeof(Boundary) + 15) & ~15;
   const size_t smem = 16 + BND_BYTES + (size_t)mask_words(cap) * 4 + (size_t)cap * 12;
-  auto kern = spmm_flat_kernel<VEC, TMA, NB, NW, MINB>;
+  auto kern = spmm_flat_kernel<VEC, TMA, NB, NW, MINB, PEERS>;
   if (smem > 48 * 1024) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid((unsigned)((k.n_tasks + NW - 1) / NW), (unsigned)k.slabs);
-  kern<<<grid, NW * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
+  PeerArg<PEERS> pa{};
+  if constexpr (PEERS) pa.s = *peers;
+  kern<<<grid, NW * 32, smem, s>>>(p, pa, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_flat_kernel");
-  return launch_fixup<VEC>(p, k, bnd, s);
+  return launch_fixup<VEC>(p, k, bnd, s, peers);
 }
 
 template <int VEC, bool TMA>
-int launch_flat_nb(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
+int launch_flat_nb(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s, const PeerSet* peers) {
   // <gathers in flight per warp / 8, warps per CTA, min CTAs per SM>.  Measured on the R-MAT config
   // (profiles/r1_variant_sweep.md): 4-warp CTAs at 64 registers (8 CTAs/SM) win; deeper per-warp
   // batches lose more to occupancy and spills than they gain in bytes in flight.
+  if (peers != nullptr) return launch_flat<VEC, TMA, 1, 4, 8, true>(p, k, bnd, s, peers);
   switch (options().pipeline) {
-    case 1: return launch_flat<VEC, TMA, 1, 8, 4>(p, k, bnd, s);
-    case 2: return launch_flat<VEC, TMA, 2, 4, 5>(p, k, bnd, s);
-    case 3: return launch_flat<VEC, TMA, 3, 4, 3>(p, k, bnd, s);
-    default: return launch_flat<VEC, TMA, 1, 4, 8>(p, k, bnd, s);
+    case 1: return launch_flat<VEC, TMA, 1, 8, 4, false>(p, k, bnd, s, nullptr);
+    case 2: return launch_flat<VEC, TMA, 2, 4, 5, false>(p, k, bnd, s, nullptr);
+    case 3: return launch_flat<VEC, TMA, 3, 4, 3, false>(p, k, bnd, s, nullptr);
+    default: return launch_flat<VEC, TMA, 1, 4, 8, false>(p, k, bnd, s, nullptr);
   }
 }
 
 template <bool STAGE>
-int dispatch(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s) {
-  if (k.lpr != 32 && (p.n_peers > 0 || p.mc != nullptr)) {
+int dispatch(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s, const PeerSet* peers) {
+  if (k.lpr != 32 && peers != nullptr) {
     set_error("the multi-GPU epilogue needs N >= 24 dense columns");
     return B200_ERR_INVALID;
   }
   if (k.lpr == 32) {
-    if (k.vec == 4) return launch_flat_nb<4, STAGE>(p, k, bnd, s);
-    if (k.vec == 2) return launch_flat_nb<2, STAGE>(p, k, bnd, s);
-    return launch_flat_nb<1, STAGE>(p, k, bnd, s);
+    if (k.vec == 4) return launch_flat_nb<4, STAGE>(p, k, bnd, s, peers);
+    if (k.vec == 2) return launch_flat_nb<2, STAGE>(p, k, bnd, s, peers);
+    return launch_flat_nb<1, STAGE>(p, k, bnd, s, peers);
   }
 #define B200_CASE(V, L) \
-  if (k.vec == V && k.lpr == L) return launch_one<V, L, STAGE>(p, k, bnd, s)
+  if (k.vec == V && k.lpr == L) return launch_one<V, L, STAGE>(p, k, bnd, s, peers)
   B200_CASE(4, 16); B200_CASE(4, 8); B200_CASE(4, 4);
   B200_CASE(2, 16); B200_CASE(2, 8); B200_CASE(2, 4);
   B200_CASE(1, 16); B200_CASE(1, 8); B200_CASE(1, 4);
@@ -593,7 +630,8 @@ int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void*
 
 // workspace layout: [partition block (unless cached)][pieces 2 * n_tasks * N]
 int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_bytes,
-                        const void* cached_part, const FwdPick* cached_pick, cudaStream_t s) {
+                        const void* cached_part, const FwdPick* cached_pick, cudaStream_t s,
+                        const PeerSet* peers) {
   FwdParams p = pin;
   if (p.M == 0 || p.N == 0) return B200_OK;
   if (p.nnz == 0) {  // all rows empty: C = 0
@@ -636,7 +674,7 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
   p.pieces = reinterpret_cast<float*>(ws + part_bytes);
   const int want_stage = (p.stage >= 0) ? p.stage : options().stage_mode;
   const bool stage = want_stage == 1 && is_aligned(p.col, 16) && is_aligned(p.val, 16);
-  return stage ? dispatch<true>(p, k, part, s) : dispatch<false>(p, k, part, s);
+  return stage ? dispatch<true>(p, k, part, s, peers) : dispatch<false>(p, k, part, s, peers);
 }
 
 }  // namespace b200
