@@ -102,6 +102,8 @@ struct b200_plan {
   bool bnd_valid[2] = {false, false};
   int t_max_row = -1;
   Boundary* sd_bnd = nullptr;  // SDDMM task boundaries (heavy threshold 0)
+  PeerSet* d_peers = nullptr;  // device copy of the peer pointers of the multi-GPU epilogue
+  PeerSet h_peers{};           // what d_peers currently holds
 };
 
 // Boundaries depend on (row_ptr, W, heavy) only: compute once per plan side, reuse for every N.
@@ -382,7 +384,7 @@ int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const f
 int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
-  cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd);
+  cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd); cudaFree(p->d_peers);
   cudaGetLastError();
   delete p;
   return B200_OK;
@@ -416,13 +418,22 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
   FwdParams q{};
   q.row_ptr = row_ptr; q.col = col; q.val = val; q.M = M; q.nnz = p->nnz;
   q.B = d_B; q.ldb = ldb; q.N = (int)N; q.C = d_C; q.ldc = ldc; q.stage = -1;
-  PeerSet ps{};
-  for (int i = 0; i < n_peers; ++i) ps.peer[i] = peer_C[i];
-  ps.n_peers = n_peers;
-  ps.mc = mc_C;
+  const PeerSet* d_peers = nullptr;
+  if (n_peers > 0 || mc_C != nullptr) {
+    PeerSet ps{};
+    for (int i = 0; i < n_peers; ++i) ps.peer[i] = peer_C[i];
+    ps.n_peers = n_peers;
+    ps.mc = mc_C;
+    if (p->d_peers == nullptr) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->d_peers), sizeof(PeerSet)));
+    if (memcmp(&ps, &p->h_peers, sizeof(PeerSet)) != 0) {  // uploaded once per set of peers, not per call
+      B200_CUDA_OK(cudaMemcpyAsync(p->d_peers, &ps, sizeof(PeerSet), cudaMemcpyHostToDevice, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      p->h_peers = ps;
+    }
+    d_peers = p->d_peers;
+  }
   return launch_spmm_forward(q, p->ws, p->ws_bytes, p->bnd_valid[side] ? p->bnd[side] : nullptr,
-                             p->bnd_valid[side] ? &p->pick[side] : nullptr, s,
-                             (n_peers > 0 || mc_C != nullptr) ? &ps : nullptr);
+                             p->bnd_valid[side] ? &p->pick[side] : nullptr, s, d_peers);
 }
 
 int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,

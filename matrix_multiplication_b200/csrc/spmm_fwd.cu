@@ -66,14 +66,14 @@ __device__ __forceinline__ void store_c(float* C, const PeerArg<PEERS>& ps, long
   if constexpr (!PEERS) {
     o.store_stream(C + off);
   } else {
-    if (ps.s.mc != nullptr) {
-      o.store_mc(ps.s.mc + off);  // the switch delivers it to every rank, this one included
+    float* mc = ps.s->mc;
+    if (mc != nullptr) {
+      o.store_mc(mc + off);  // the switch delivers it to every rank, this one included
       return;
     }
     o.store_stream(C + off);
-#pragma unroll
-    for (int q = 0; q < 7; ++q)  // static indices: the pointers stay in the constant bank
-      if (q < ps.s.n_peers) o.store_stream(ps.s.peer[q] + off);
+    const int n_peers = ps.s->n_peers;
+    for (int q = 0; q < n_peers; ++q) o.store_stream(ps.s->peer[q] + off);
   }
 }
 
@@ -499,7 +499,7 @@ int launch_fixup(const FwdParams& p, const FwdPick& k, const void* part, cudaStr
   if (k.n_tasks <= 1 || !k.may_split) return B200_OK;
   const int slabs = (p.N + 32 * VEC - 1) / (32 * VEC);
   dim3 fgrid((unsigned)std::min(148 * 8, k.n_tasks), (unsigned)slabs);
-  if (peers != nullptr) spmm_fixup_kernel<VEC, true><<<fgrid, 256, 0, s>>>(p, PeerArg<true>{*peers}, part, k.W, k.n_tasks);
+  if (peers != nullptr) spmm_fixup_kernel<VEC, true><<<fgrid, 256, 0, s>>>(p, PeerArg<true>{peers}, part, k.W, k.n_tasks);
   else spmm_fixup_kernel<VEC, false><<<fgrid, 256, 0, s>>>(p, PeerArg<false>{0}, part, k.W, k.n_tasks);
   B200_LAUNCH_OK("spmm_fixup_kernel");
   return B200_OK;
@@ -532,7 +532,7 @@ int launch_flat(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStrea
   }
   dim3 grid((unsigned)((k.n_tasks + NW - 1) / NW), (unsigned)k.slabs);
   PeerArg<PEERS> pa{};
-  if constexpr (PEERS) pa.s = *peers;
+  if constexpr (PEERS) pa.s = peers;
   kern<<<grid, NW * 32, smem, s>>>(p, pa, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_flat_kernel");
   return launch_fixup<VEC>(p, k, bnd, s, peers);
