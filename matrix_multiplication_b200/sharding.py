@@ -17,8 +17,11 @@ import numpy as np
 from . import _capi as capi
 
 
-def shard_bounds(row_ptr, parts: int, N: int, miss: float = 0.5) -> np.ndarray:
-    '''Row boundaries (parts + 1 entries) of cost-balanced contiguous shards.'''
+def shard_bounds(row_ptr, parts: int, N: int, miss: float = 0.29) -> np.ndarray:
+    '''Row boundaries (parts + 1 entries) of cost-balanced contiguous shards.
+
+    ``miss`` sets the relative price of a gathered B row against a written C row; 0.29 reproduces the
+    measured per-shard times on the R-MAT config (benchmarks/shard_balance.py: one row costs about 3.3 non-zeros).'''
     if parts <= 1:
         return np.array([0, len(row_ptr) - 1], dtype=np.int64)
     return capi.shard_rows(row_ptr, parts, 8.0 + 4.0 * N * miss, 4.0 * N)
