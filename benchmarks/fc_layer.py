@@ -99,10 +99,34 @@ def main():
             d2(torch.relu(d1(x))).sum().backward()
 
         # parity of the arms before timing
-        y_e = l2(torch.relu(l1(x)))
-        y_d = d2(torch.relu(d1(x)))
+        with torch.no_grad():  # (no autograd graph may outlive this line: CUDA-graph capture below)
+            y_e = l2(torch.relu(l1(x)))
+            y_d = d2(torch.relu(d1(x)))
         rel = float((y_e - y_d).abs().max() / y_d.abs().max())
         r = {"config": name, "nnz": nnz, "tokens": tokens, "rel_diff_vs_dense": rel}
+        # the same engine step captured once in a CUDA graph and replayed (launch-bound configs: one launch per step)
+        try:
+            for p in (l1.values, l2.values, l1.bias, l2.bias):
+                p.grad = None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_engine_t()
+            torch.cuda.current_stream().wait_stream(side)
+            for p in (l1.values, l2.values, l1.bias, l2.bias):
+                p.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                l2.forward_t(torch.relu(l1.forward_t(xT))).sum().backward()
+            graph.replay()
+            torch.cuda.synchronize()
+            g_graph = l1.values.grad.clone()
+            step_engine_t()
+            r["graph_grad_rel_diff"] = float((g_graph - l1.values.grad).abs().max() / l1.values.grad.abs().max())
+            r["engine_T_graph_ms"] = timeit(graph.replay, args.iters)
+        except Exception as e:
+            r["engine_T_graph_error"] = f"{type(e).__name__}: {str(e)[:160]}"
         r["engine_ms"] = timeit(step_engine, args.iters)
         r["engine_T_ms"] = timeit(step_engine_t, args.iters)
         try:
