@@ -552,9 +552,13 @@ def main():
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (b200_set_option)")
     ap.add_argument("--traffic", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture")
+                    help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture "
+                         "(default: the committed figure for the default workload on 1 GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.traffic is None and args.workload == "c4" and args.scale is None and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        # dram__bytes_read.sum + dram__bytes_write.sum of spmm_flat_kernel, profiles/r1_ncu_fwd_c4.md
+        args.traffic = 1.553385e9 + 0.505407e9
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -3,9 +3,13 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs; the product never imports it.
 
-Parity status: PINNED — tests/test_oracle.py checks every function here against the fixtures
-in tests/golden/ that tests/golden/make_golden.py generated by importing the reference's
-matmuls.py (/root/reference/matmuls.py) in the build container.
+Parity status: PINNED — tests/test_oracle.py checks every function here against
+  (i)  tests/golden/ref_*.npz: outputs of the REAL reference (oracle/_ref = its own custom_mm + matmuls, nothing
+       stubbed) recorded on a B200 by tests/golden/make_ref_golden.py — cuSPARSE forward on the reference's five
+       test shapes, its naive kernel (reproduced bit for bit by spmm_f32), its grad_m2, and the CSR arrays its
+       get_sparse_tensor_properties built;
+  (ii) tests/golden/{fwd,naive,csr,bwd}_*.npz: generated in the build container by importing the reference's
+       matmuls.py against a stub custom_mm (tests/golden/make_golden.py) — shape dispatch and edge-case CSRs.
 
 Each function names the reference lines it restates (paths relative to /root/reference).
 """

@@ -3,7 +3,9 @@
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this; the product (libspmm_b200.so, custom_mm, matmuls) never does.
  *
- * Parity status: PINNED against fixtures generated from the reference's own Python layer
+ * Parity status: PINNED — against outputs of the real reference recorded on a B200
+ * (tests/golden/ref_*.npz, tests/golden/make_ref_golden.py: cuSPARSE forward, naive kernel, grad_m2, CSR arrays)
+ * and against fixtures generated from the reference's own Python layer in the build container
  * (tests/golden/make_golden.py imports /root/reference/matmuls.py and records what
  * `a.to_sparse_csr()` + its int32 casts and `sparse_matmul` produce) — see
  * tests/test_oracle.py.  The reference's arithmetic itself lives in cuSPARSE 12.5
