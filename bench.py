@@ -458,6 +458,10 @@ def run_ours(args):
         "e2e": {"value": round(flops(w) / (e2e_ms * 1e-3) / 1e9, 2), "unit": "GFLOP/s",
                 "h2d_bytes_per_step": int(B_host.numel() * 4) * world, "d2h_bytes_per_step": int(M * N * 4),
                 "ms_per_step": round(e2e_ms, 4), "api": "matmuls.cusparseMM.apply(a_csr, b)"},
+        # what actually limits this workload: every non-zero pulls an N*4-byte B row L2 -> SM;
+        # ceiling = best rate of tools/l2bw.cu for 512-byte rows with the same column skew (profiles/r1_variant_sweep.md)
+        "binding_roof": {"name": "L2->SM gather of B rows", "bytes": int((p1 - p0)) * N * 4,
+                         "achieved_TBs": round((p1 - p0) * N * 4 / (k_ms * 1e-3) / 1e12, 2), "measured_ceiling_TBs": 20.25},
         "gpu_launches": int(launches), "clocks": clk.summary(), "parity_rel_err_vs_fp64_oracle": parity,
         "wall_ms_per_step": round(wall_ms / args.steps, 5),
         "comparators": comp,
