@@ -170,6 +170,13 @@ int b200_plan_backward_A(b200_plan* plan, const float* d_G, int64_t ldg,
                          const float* d_B, int64_t ldb, int64_t N,
                          float* d_dval, void* stream);
 
+/* End-to-end forward with HOST buffers on a resident plan: C_host[M,N] = A * B_host[K,N].
+ * B is cut into `panels` column panels (0 = auto); the upload of panel p+1, the product of panel p and the
+ * download of panel p-1 run concurrently on three streams (PCIe is full duplex; C[:, panel] needs only
+ * B[:, panel]), so a step costs about max(H2D, D2H) instead of H2D + product + D2H.  h_B / h_C should be pinned
+ * (cudaHostAlloc / cudaHostRegister) — pageable memory works but serialises.  Returns after C is in host memory. */
+int b200_plan_forward_host(b200_plan* plan, const float* h_B, int64_t N, float* h_C, int panels);
+
 /* ---- host-buffer convenience entry points (end-to-end path) --------------------
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous).
  * Each call copies its inputs to the device, runs the device path above and

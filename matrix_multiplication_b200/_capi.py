@@ -61,6 +61,7 @@ SIGNATURES = {
     "b200_plan_values_updated": (C.c_int, [_vp]),
     "b200_plan_stats": (C.c_int, [_vp, _i64p, _i64p]),
     "b200_plan_forward": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "b200_plan_forward_host": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int]),
     "b200_plan_forward_peers": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), C.c_int, _vp, _vp]),
     "b200_plan_backward_B": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b200_plan_backward_A": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
@@ -262,6 +263,15 @@ class Plan:
         N = B.shape[1]
         check(lib().b200_plan_forward(self._h, _dp(B), N, N, _dp(Cout), N, C.c_void_p(stream)))
         return Cout
+
+    def forward_host(self, B_host, C_host, panels=0):
+        """End-to-end forward with (pinned) HOST buffers — numpy arrays or CPU torch tensors; uploads, the product
+        and downloads are pipelined over column panels inside the library.  Returns when C_host is complete."""
+        N = B_host.shape[1]
+        pb = B_host.data_ptr() if hasattr(B_host, "data_ptr") else B_host.ctypes.data
+        pc = C_host.data_ptr() if hasattr(C_host, "data_ptr") else C_host.ctypes.data
+        check(lib().b200_plan_forward_host(self._h, C.c_void_p(pb), N, C.c_void_p(pc), panels))
+        return C_host
 
     def forward_peers(self, B, Cout, peer_ptrs=(), mc_ptr=0, stream=0):
         """Forward whose epilogue also stores every row into peers' buffers (raw device addresses of THIS

@@ -102,6 +102,10 @@ struct b200_plan {
   bool bnd_valid[2] = {false, false};
   int t_max_row = -1;
   Boundary* sd_bnd = nullptr;  // SDDMM task boundaries (heavy threshold 0)
+  // host-buffer pipeline (b200_plan_forward_host): device B / C, three streams, per-panel events
+  float* hB = nullptr; float* hC = nullptr; size_t hB_bytes = 0, hC_bytes = 0;
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t hev[2][16] = {};
   PeerSet* d_peers = nullptr;  // device copy of the peer pointers of the multi-GPU epilogue
   PeerSet h_peers{};           // what d_peers currently holds
 };
@@ -385,6 +389,9 @@ int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
   cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd); cudaFree(p->d_peers);
+  cudaFree(p->hB); cudaFree(p->hC);
+  for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
+  for (int j = 0; j < 2; ++j) for (int i = 0; i < 16; ++i) if (p->hev[j][i]) cudaEventDestroy(p->hev[j][i]);
   cudaGetLastError();
   delete p;
   return B200_OK;
@@ -441,6 +448,55 @@ int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, fl
   B200_REQUIRE(p != nullptr, "null plan");
   return plan_spmm(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc,
                    (cudaStream_t)stream);
+}
+
+int b200_plan_forward_host(b200_plan* p, const float* h_B, int64_t N, float* h_C, int panels) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  if (p->M == 0 || N == 0) return B200_OK;
+  B200_REQUIRE(h_C != nullptr && (p->nnz == 0 || h_B != nullptr), "null host pointer");
+  // panels: multiples of 32 columns (one 128-byte line per B row and panel at least), at most 16
+  // auto: panels of >= 64 columns (narrower 2-D PCIe copies lose more than the extra overlap gains; measured
+  // with tools/host_pipeline_check.py: 1 / 2 / 4 panels of a 128-column operand = 4.97 / 3.96 / 4.45 ms)
+  if (panels <= 0) panels = (int)std::min<int64_t>(4, std::max<int64_t>(1, N / 64));
+  while (panels > 1 && (N % panels != 0 || (N / panels) % 32 != 0)) --panels;
+  if (panels > 16) panels = 16;
+  const int64_t w = N / panels;
+  const size_t bB = (size_t)p->K * N * sizeof(float), bC = (size_t)p->M * N * sizeof(float);
+  if (p->hB_bytes < bB) {
+    if (p->hB) { B200_CUDA_OK(cudaDeviceSynchronize()); B200_CUDA_OK(cudaFree(p->hB)); p->hB = nullptr; p->hB_bytes = 0; }
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->hB), std::max<size_t>(bB, 16)));
+    p->hB_bytes = bB;
+  }
+  if (p->hC_bytes < bC) {
+    if (p->hC) { B200_CUDA_OK(cudaDeviceSynchronize()); B200_CUDA_OK(cudaFree(p->hC)); p->hC = nullptr; p->hC_bytes = 0; }
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->hC), std::max<size_t>(bC, 16)));
+    p->hC_bytes = bC;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (!p->hs[i]) B200_CUDA_OK(cudaStreamCreateWithFlags(&p->hs[i], cudaStreamNonBlocking));
+  for (int j = 0; j < 2; ++j)
+    for (int i = 0; i < panels; ++i)
+      if (!p->hev[j][i]) B200_CUDA_OK(cudaEventCreateWithFlags(&p->hev[j][i], cudaEventDisableTiming));
+  const size_t pitch = (size_t)N * sizeof(float);
+  for (int i = 0; i < panels; ++i) {
+    const size_t off = (size_t)i * w;
+    if (p->nnz > 0) {
+      B200_CUDA_OK(cudaMemcpy2DAsync(p->hB + off, pitch, h_B + off, pitch, (size_t)w * sizeof(float), (size_t)p->K,
+                                     cudaMemcpyHostToDevice, p->hs[0]));
+    }
+    B200_CUDA_OK(cudaEventRecord(p->hev[0][i], p->hs[0]));
+    B200_CUDA_OK(cudaStreamWaitEvent(p->hs[1], p->hev[0][i], 0));
+    int rc = plan_spmm(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, p->hB + off, N, w, p->hC + off, N,
+                       p->hs[1]);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaEventRecord(p->hev[1][i], p->hs[1]));
+    B200_CUDA_OK(cudaStreamWaitEvent(p->hs[2], p->hev[1][i], 0));
+    B200_CUDA_OK(cudaMemcpy2DAsync(h_C + off, pitch, p->hC + off, pitch, (size_t)w * sizeof(float), (size_t)p->M,
+                                   cudaMemcpyDeviceToHost, p->hs[2]));
+  }
+  B200_CUDA_OK(cudaStreamSynchronize(p->hs[2]));
+  return B200_OK;
 }
 
 int b200_plan_forward_peers(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,

@@ -330,3 +330,25 @@ def test_engine_matches_recorded_reference_backward():
     shape = tuple(int(x) for x in g["shape"])
     gb = capi.backward_B_host(g["row_ptr"], g["col"], g["val"], shape, g["G"])
     assert oracle.rel_err(gb, g["grad_B"].astype(np.float64)) <= TOL
+
+
+@pytest.mark.parametrize("N,panels", [(128, 0), (128, 2), (96, 0), (40, 0), (256, 8)])
+def test_plan_forward_host_pipeline(N, panels):
+    """b200_plan_forward_host: column-panel pipeline with host buffers (pinned and pageable)."""
+    import torch
+    rng = np.random.default_rng(N)
+    M, K = 900, 1100
+    rp, ci, va, _ = random_csr(rng, M, K, 0.02, heavy_rows=(4,), empty_rows=(0, 899))
+    dev = torch.device("cuda:0")
+    crow, col, val = (torch.from_numpy(x).to(dev) for x in (rp, ci, va))
+    plan = capi.Plan(crow, col, val, (M, K))
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    ref = oracle.spmm_f64(rp, ci, va, (M, K), B)
+    Bp = torch.from_numpy(B).pin_memory()
+    Cp = torch.empty(M, N).pin_memory()
+    plan.forward_host(Bp, Cp, panels)
+    assert oracle.rel_err(Cp.numpy(), ref) <= TOL
+    Cn = np.empty((M, N), dtype=np.float32)          # pageable numpy buffers work too
+    plan.forward_host(B, Cn, panels)
+    np.testing.assert_array_equal(bits(Cn), bits(Cp.numpy()))
+    plan.close()
