@@ -31,8 +31,8 @@ sddmm_partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, i
   if (t <= n_tasks) out[t] = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, 0);
 }
 
-template <int VEC, bool TMA>
-__global__ void __launch_bounds__(SD_NW * 32, 4)
+template <int VEC, bool TMA, bool MULTI>
+__global__ void __launch_bounds__(SD_NW * 32, MULTI ? 3 : 5)
 sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int nnz,
              const float* __restrict__ G, unsigned ldg, const float* __restrict__ B, unsigned ldb, int N,
              float* __restrict__ out, const Boundary* __restrict__ bnd, int W, int n_tasks) {
@@ -79,7 +79,7 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
   if (j1 <= j0) return;
 
   const int slab_w = 32 * VEC;
-  const int n_slabs = (N + slab_w - 1) / slab_w;
+  const int n_slabs = MULTI ? (N + slab_w - 1) / slab_w : 1;  // MULTI: N wider than one slab of 32 * VEC columns
   int cur_row = -1;   // row whose G slab is cached in gcur (reused across chunks only when n_slabs == 1)
   Vec<VEC> gcur;
 #pragma unroll
@@ -99,12 +99,42 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
 #pragma unroll
     for (int k = 0; k < 8; ++k) d[k] = 0.f;
 
+    const bool one_row = vm == 0xffu && r[0] == r[7];  // rows are sorted: the whole chunk is in one row
+    if (MULTI && one_row) {
+      // wide N: walk the slabs two deep — the gathers of slab s+1 are in flight while slab s is consumed
+      auto load_slab = [&](int s, Vec<VEC>(&b)[8], Vec<VEC>& g) {
+        const int col0 = s * slab_w + lane * VEC;
+        const bool active = col0 < N;
+        const int cc = active ? col0 : 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[k].load(B + (unsigned long long)(unsigned)c[k] * ldb + cc);
+        g.load(G + (unsigned long long)(unsigned)r[0] * ldg + cc);
+        if (!active) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) g.v[v] = 0.f;
+        }
+      };
+      auto fma_slab = [&](const Vec<VEC>(&b)[8], const Vec<VEC>& g) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[k] = fmaf(g.v[v], b[k].v[v], d[k]);
+      };
+      Vec<VEC> b0[8], b1[8], g0, g1;
+      load_slab(0, b0, g0);
+      for (int s = 0; s < n_slabs; s += 2) {
+        if (s + 1 < n_slabs) load_slab(s + 1, b1, g1);
+        fma_slab(b0, g0);
+        if (s + 2 < n_slabs) load_slab(s + 2, b0, g0);
+        if (s + 1 < n_slabs) fma_slab(b1, g1);
+      }
+      cur_row = -1;
+    } else
     for (int s = 0; s < n_slabs; ++s) {
       const int col0 = s * slab_w + lane * VEC;
       const bool active = col0 < N;
       const int cc = active ? col0 : 0;  // inactive lanes read column 0 and contribute 0
       Vec<VEC> b[8];
-      const bool one_row = vm == 0xffu && r[0] == r[7];  // rows are sorted: the whole chunk is in one row
       if (one_row) {  // one G slab serves all 8 non-zeros (kept in registers across chunks when N fits one slab)
 #pragma unroll
         for (int k = 0; k < 8; ++k) b[k].load(B + (unsigned long long)(unsigned)c[k] * ldb + cc);
@@ -265,7 +295,7 @@ int launch_grouped(const int* row_ptr, const int* col, int M, int nnz, const flo
 
 inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int VEC, bool TMA>
+template <int VEC, bool TMA, bool MULTI>
 int launch_one(const int* row_ptr, const int* col, int M, int nnz, const float* G, long long ldg,
                const float* B, long long ldb, int N, float* out, const Boundary* bnd, int n_tasks,
                cudaStream_t s) {
@@ -274,7 +304,7 @@ int launch_one(const int* row_ptr, const int* col, int M, int nnz, const float* 
   constexpr int BND_BYTES = ((SD_NW + 1) * (int)sizeof(Boundary) + 15) & ~15;
   const size_t smem = 16 + BND_BYTES + (size_t)cap * 8;
   dim3 grid((unsigned)((n_tasks + SD_NW - 1) / SD_NW));
-  sddmm_kernel<VEC, TMA><<<grid, SD_NW * 32, smem, s>>>(row_ptr, col, M, nnz, G, (unsigned)ldg, B,
+  sddmm_kernel<VEC, TMA, MULTI><<<grid, SD_NW * 32, smem, s>>>(row_ptr, col, M, nnz, G, (unsigned)ldg, B,
                                                          (unsigned)ldb, N, out, bnd, W, n_tasks);
   B200_LAUNCH_OK("sddmm_kernel");
   return B200_OK;
@@ -343,13 +373,16 @@ int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float
   int vec = 1;
   while (vec < vmax && 32 * vec < N) vec <<= 1;
   const bool tma = is_aligned(col, 16);
-#define B200_SD(V)                                                                                     \
-  if (vec == V)                                                                                        \
-    return tma ? launch_one<V, true>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, bnd, n_tasks, s)    \
-               : launch_one<V, false>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, bnd, n_tasks, s)
+  const bool multi = N > 32 * vec;
+#define B200_SD2(V, T, MU) launch_one<V, T, MU>(row_ptr, col, M, nnz, G, ldg, B, ldb, N, out, bnd, n_tasks, s)
+#define B200_SD(V)                                                                       \
+  if (vec == V)                                                                          \
+    return tma ? (multi ? B200_SD2(V, true, true) : B200_SD2(V, true, false))            \
+               : (multi ? B200_SD2(V, false, true) : B200_SD2(V, false, false))
   B200_SD(4);
   B200_SD(2);
   B200_SD(1);
+#undef B200_SD2
 #undef B200_SD
   return B200_ERR_INVALID;
 }
