@@ -135,6 +135,13 @@ int b200_dense_to_csr_alloc(const float* d_dense, int64_t M, int64_t K, int64_t 
                             int64_t* nnz, void* stream);
 int b200_free_csr(float* d_val, int32_t* d_col_ind, int32_t* d_row_ptr);
 
+/* Batched operands: a stack of L dense [M,K] matrices converted as ONE [L*M, K] matrix (b200_dense_to_csr_*)
+ * becomes the block-diagonal CSR of shape [L*M, L*K] by shifting the columns of row r by (r / M) * K.
+ * One SpMM against the stacked dense operand [L*K, N] then replaces the per-sample loop of the reference
+ * (matmuls.py:221-225, 289-293).  In place on d_col_ind; L*K must fit int32. */
+int b200_csr_block_diag_cols(const int32_t* d_row_ptr, int32_t* d_col_ind, int64_t rows, int64_t M, int64_t K,
+                             void* stream);
+
 /* ---- plans: the inspect / execute / clean triple -------------------------------
  * A plan borrows a device CSR, owns its scratch, and lazily builds + caches the
  * transposed CSR used by backward_B.  Not thread-safe per plan. */

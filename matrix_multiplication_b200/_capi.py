@@ -56,6 +56,7 @@ SIGNATURES = {
     "b200_dense_to_csr_alloc": (C.c_int, [_vp, _i64, _i64, _i64, C.POINTER(_vp), C.POINTER(_vp),
                                           C.POINTER(_vp), _i64p, _vp]),
     "b200_free_csr": (C.c_int, [_vp, _vp, _vp]),
+    "b200_csr_block_diag_cols": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "b200_plan_create": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, C.POINTER(_vp), _vp]),
     "b200_plan_destroy": (C.c_int, [_vp]),
     "b200_plan_values_updated": (C.c_int, [_vp]),

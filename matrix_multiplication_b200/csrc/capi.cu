@@ -350,6 +350,16 @@ int b200_free_csr(float* d_val, int32_t* d_col_ind, int32_t* d_row_ptr) {
   return B200_OK;
 }
 
+int b200_csr_block_diag_cols(const int32_t* d_row_ptr, int32_t* d_col_ind, int64_t rows, int64_t M, int64_t K,
+                             void* stream) {
+  B200_REQUIRE(rows >= 0 && M > 0 && K >= 0 && rows < 0x7fffffffLL, "bad dimensions");
+  B200_REQUIRE(rows % M == 0, "rows must be a multiple of M");
+  B200_REQUIRE((rows / M) * K < 0x7fffffffLL, "L * K exceeds the int32 column range");
+  if (rows == 0) return B200_OK;
+  B200_REQUIRE(d_row_ptr != nullptr && d_col_ind != nullptr, "null CSR pointer");
+  return launch_block_diag(d_row_ptr, d_col_ind, (int)rows, (int)M, (int)K, (cudaStream_t)stream);
+}
+
 // ---- plans ---------------------------------------------------------------------------
 int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val, int64_t M,
                      int64_t K, int64_t nnz, b200_plan** out_plan, void* stream) {

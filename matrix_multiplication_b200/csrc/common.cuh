@@ -253,6 +253,7 @@ int launch_dense_count(const float* dense, int M, int K, long long ld, int* row_
 int launch_dense_fill(const float* dense, int M, int K, long long ld, const int* row_ptr, int* col,
                       float* val, cudaStream_t s);
 int launch_row_stats(const int* row_ptr, int M, int* d_out2 /* max_len, empty */, cudaStream_t s);
+int launch_block_diag(const int* row_ptr, int* col, int rows, int M, int K, cudaStream_t s);
 
 // per-device cached scratch (grown on demand; stream-ordered use only)
 int get_scratch(size_t bytes, void** ptr);

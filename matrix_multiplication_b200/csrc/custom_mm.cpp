@@ -305,6 +305,15 @@ std::vector<torch::Tensor> dense_to_csr(torch::Tensor dense) {
   return {crow, col, val};
 }
 
+// A stack of L dense [M,K] matrices ([L*M, K] view) -> block-diagonal CSR [L*M, L*K] on the device.
+std::vector<torch::Tensor> dense_to_csr_block_diag(torch::Tensor dense2d, int64_t M) {
+  auto out = dense_to_csr(dense2d);
+  const int64_t rows = dense2d.size(0), K = dense2d.size(1);
+  c10::cuda::CUDAGuard guard(dense2d.device());
+  check(b200_csr_block_diag_cols(out[0].data_ptr<int>(), out[1].data_ptr<int>(), rows, M, K, cur_stream()));
+  return out;
+}
+
 std::vector<torch::Tensor> csr_transpose(torch::Tensor offsets, torch::Tensor columns, torch::Tensor values,
                                          int64_t M, int64_t K) {
   const int64_t nnz = values.numel();
@@ -378,6 +387,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   // engine extras
   m.def("dense_to_csr", &dense_to_csr, "dense [M,K] -> (crow int32, col int32, val) on the device");
+  m.def("dense_to_csr_block_diag", &dense_to_csr_block_diag,
+        "stack of L dense [M,K] matrices given as [L*M,K] -> block-diagonal CSR (crow, col, val) of [L*M, L*K]");
   m.def("csr_transpose", &csr_transpose, "CSR(A) -> (crow, col, val, perm) of A^T");
   m.def("gather", &gather, "out[q] = src[perm[q]]");
   m.def("sddmm", &sddmm, "grad of CSR values: sum_j G[row,j] * B[col,j] on A's pattern");

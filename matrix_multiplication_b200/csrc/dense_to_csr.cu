@@ -145,6 +145,19 @@ __global__ void row_stats_kernel(const int* __restrict__ row_ptr, int M, int* __
   }
 }
 
+// col[p] += (row / M) * K for every non-zero of every row: warp per row
+__global__ void __launch_bounds__(256)
+block_diag_kernel(const int* __restrict__ row_ptr, int* __restrict__ col, int rows, int M, int K) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps_per_grid) {
+    const int shift = (row / M) * K;
+    if (shift == 0) continue;
+    const int e = __ldg(row_ptr + row + 1);
+    for (int p = __ldg(row_ptr + row) + lane; p < e; p += 32) col[p] += shift;
+  }
+}
+
 inline int warp_grid(int M) {
   long long ctas = ((long long)M + 7) / 8;  // 8 warps per CTA, one row per warp
   long long cap = 148LL * 8;
@@ -172,6 +185,13 @@ int launch_dense_fill(const float* dense, int M, int K, long long ld, const int*
   if (M == 0 || K == 0) return B200_OK;
   fill_kernel<<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr, col, val);
   B200_LAUNCH_OK("dense_fill_kernel");
+  return B200_OK;
+}
+
+int launch_block_diag(const int* row_ptr, int* col, int rows, int M, int K, cudaStream_t s) {
+  if (rows == 0) return B200_OK;
+  block_diag_kernel<<<warp_grid(rows), 256, 0, s>>>(row_ptr, col, rows, M, K);
+  B200_LAUNCH_OK("block_diag_kernel");
   return B200_OK;
 }
 

@@ -19,7 +19,9 @@ What changed underneath (SURVEY.md §3, §9 — reference defects are not reprod
   grad_C * b^T through the cuBLAS path;
 * non-contiguous operands are made contiguous instead of being reinterpreted;
 * 2-D x 3-D and 3-D x 2-D shapes are computed with one launch instead of a wrong
-  reshape / a silent ``a @ b`` (matmuls.py:213-220, 230-234).
+  reshape / a silent ``a @ b`` (matmuls.py:213-220, 230-234);
+* N-D x N-D batches run as ONE launch over a block-diagonal CSR instead of a Python loop
+  over the batch (matmuls.py:221-225, 289-293).
 '''
 
 import warnings
@@ -288,7 +290,17 @@ def _sparse_dispatch(a, b, mm_op):
         lead, (M, K) = a.shape[:-2], a.shape[-2:]
         return _spmm_2d(a.reshape(-1, K), b, mm_op).reshape(*lead, M, b.shape[-1])
     if a_dim == b.dim():
-        assert a.shape[0] == b.shape[0], 'batch dimensions differ'
+        # a batch of independent (A_l, B_l) pairs: ONE launch over the block-diagonal CSR of the stacked A
+        # against the stacked B (the reference loops over the batch in Python, matmuls.py:221-225, 289-293)
+        assert a.shape[:-2] == b.shape[:-2], 'batch dimensions differ'
+        lead, (M, K), N = a.shape[:-2], a.shape[-2:], b.shape[-1]
+        L = 1
+        for s in lead:
+            L *= s
+        if L * K < 2 ** 31 and L * M < 2 ** 31:
+            crow, col, val = custom_mm.dense_to_csr_block_diag(a.reshape(L * M, K).to(torch.float32).contiguous(), M)
+            m = CsrMatrix(crow, col, val, (L * M, L * K))
+            return _spmm_2d(m, b.reshape(L * K, N), mm_op).reshape(*lead, M, N)
         return torch.stack([_sparse_dispatch(a[i], b[i], mm_op) for i in range(a.shape[0])])
     raise ValueError(f'unsupported operand ranks {a_dim} x {b.dim()}')
 

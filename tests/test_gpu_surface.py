@@ -227,3 +227,27 @@ def test_fc_layer_like_the_reference_benchmark(mods):
     mask = fc1.dense_weight() != 0
     assert float((got - gw1 * mask).abs().max() / gw1.abs().max()) <= 1e-5
     assert float((fc1.bias.grad.double() - gh.sum(0)).abs().max() / gh.sum(0).abs().max()) <= 1e-5
+
+
+def test_batched_product_is_one_launch(mods):
+    """N-D x N-D: the reference loops over the batch in Python (matmuls.py:221-225; its own test drives 4096
+    sequential calls, tests/naive_kernel_test.py:67).  Here the batch is one block-diagonal SpMM."""
+    torch, custom_mm, matmuls = mods
+    torch.manual_seed(5)
+    a = torch.rand(16, 4, 64, 64, device="cuda") * (torch.rand(16, 4, 64, 64, device="cuda") < 0.2)
+    b = torch.rand(16, 4, 64, 32, device="cuda")
+    matmuls.naiveSpMM.apply(a, b)  # warm-up (scratch buffers)
+    n0 = custom_mm.kernel_launch_count()
+    out = matmuls.naiveSpMM.apply(a, b)
+    launches = custom_mm.kernel_launch_count() - n0
+    assert launches <= 8, f"{launches} kernel launches for one batched product"
+    expected = (a.double() @ b.double()).float()
+    assert out.shape == expected.shape
+    assert torch.allclose(expected, out, rtol=1e-5, atol=1e-6)
+    # gradients through the batched wrapper
+    a2 = a.clone().requires_grad_(True)
+    b2 = b.clone().requires_grad_(True)
+    matmuls.cusparseMM.apply(a2, b2).sum().backward()
+    ones = torch.ones_like(expected).double()
+    assert torch.allclose(b2.grad.double(), a.double().transpose(-1, -2) @ ones, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(a2.grad.double(), ones @ b.double().transpose(-1, -2), rtol=1e-4, atol=1e-4)
