@@ -314,7 +314,7 @@ int launch_one(const int* row_ptr, const int* col, int M, int nnz, const float* 
 
 namespace {
 int sd_items(long long M, long long nnz) {  // same rule as the forward: spread small problems over the SMs
-  const long long spread = (M + nnz) / (148 * 8);
+  const long long spread = (M + nnz) / (148 * 96);
   const int W = (int)std::min<long long>(SD_W, std::max<long long>(32, spread));
   return (W + 31) & ~31;
 }
