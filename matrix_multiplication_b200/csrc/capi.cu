@@ -430,7 +430,7 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
   B200_REQUIRE(d_C != nullptr && (p->nnz == 0 || d_B != nullptr), "null B / C");
   int rc = plan_ensure_bounds(p, side, row_ptr, M, max_row, N, s);
   if (rc) return rc;
-  rc = plan_ensure_ws(p, fwd_workspace_bytes(std::max(p->M, p->K), p->nnz, N));
+  rc = plan_ensure_ws(p, fwd_workspace_bytes(M, p->nnz, N));  // exact for this side (the task size depends on M + nnz)
   if (rc) return rc;
   FwdParams q{};
   q.row_ptr = row_ptr; q.col = col; q.val = val; q.M = M; q.nnz = p->nnz;

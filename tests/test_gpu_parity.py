@@ -352,3 +352,34 @@ def test_plan_forward_host_pipeline(N, panels):
     plan.forward_host(B, Cn, panels)
     np.testing.assert_array_equal(bits(Cn), bits(Cp.numpy()))
     plan.close()
+
+
+@pytest.mark.parametrize("M,K", [(3000, 250000), (250000, 3000)])
+def test_plan_very_rectangular(M, K):
+    """Row shards of a big matrix are very rectangular (few rows, all the columns): the task size — and with it
+    the workspace — differs between the forward (M + nnz items) and the transposed product (K + nnz items)."""
+    import torch
+    rng = np.random.default_rng(M)
+    nnz = 400000
+    rows = np.sort(rng.integers(0, M, nnz))
+    cols = rng.integers(0, K, nnz)
+    key = np.unique(rows.astype(np.int64) * K + cols)
+    rows, cols = (key // K).astype(np.int64), (key % K).astype(np.int32)
+    rp = np.zeros(M + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=M), out=rp[1:])
+    rp = rp.astype(np.int32)
+    va = rng.standard_normal(len(cols)).astype(np.float32)
+    N = 64
+    dev = torch.device("cuda:0")
+    crow, col, val = (torch.from_numpy(x).to(dev) for x in (rp, cols, va))
+    B = torch.from_numpy(rng.standard_normal((K, N)).astype(np.float32)).to(dev)
+    G = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).to(dev)
+    plan = capi.Plan(crow, col, val, (M, K))
+    C = plan.forward(B, torch.empty(M, N, device=dev))
+    dB = plan.backward_B(G, torch.empty(K, N, device=dev))
+    dA = plan.backward_A(G, B, torch.empty(len(va), device=dev))
+    torch.cuda.synchronize()
+    assert oracle.rel_err(C.cpu().numpy(), oracle.spmm_f64(rp, cols, va, (M, K), B.cpu().numpy())) <= TOL
+    assert oracle.rel_err(dB.cpu().numpy(), oracle.spmm_t_f64(rp, cols, va, (M, K), G.cpu().numpy())) <= TOL
+    assert oracle.rel_err(dA.cpu().numpy(), oracle.sddmm_f64(rp, cols, (M, K), G.cpu().numpy(), B.cpu().numpy())) <= TOL
+    plan.close()
