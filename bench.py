@@ -449,6 +449,27 @@ def run_ours(args):
             dist.barrier(); dist.destroy_process_group()
         return
 
+    # ---- backward of the same product (north_star: forward + backward), single GPU only ---------------------
+    phases = None
+    if world == 1:
+        from matrix_multiplication_b200 import synthetic
+        Gd = torch.rand(M, N, device=dev)
+        dB = torch.empty(K, N, device=dev)
+        dA = torch.empty(nnz, device=dev)
+        plan.backward_B(Gd, dB, stream=stream)  # builds + caches the transposed CSR (inspector time, not timed)
+        gb_ms, _ = timed_region(lambda: plan.backward_B(Gd, dB, stream=stream), args.steps, args.warmup, None, flush)
+        ga_ms, _ = timed_region(lambda: plan.backward_A(Gd, B, dA, stream=stream), args.steps, args.warmup, None, flush)
+        gb_ms, ga_ms = gb_ms / args.steps, ga_ms / args.steps
+        by = (synthetic.spmm_algorithmic_bytes(M, K, nnz, N) + synthetic.spmm_algorithmic_bytes(K, M, nnz, N)
+              + synthetic.sddmm_algorithmic_bytes(M, K, nnz, N))
+        tot = ms_per_step + gb_ms + ga_ms
+        phases = {"forward_ms": round(ms_per_step, 5), "grad_B_spmm_over_cached_transpose_ms": round(gb_ms, 5),
+                  "grad_A_sddmm_ms": round(ga_ms, 5), "fwd_bwd_ms": round(tot, 5),
+                  "fwd_bwd_gflops": round(3 * flops(w) / (tot * 1e-3) / 1e9, 1),
+                  "fwd_bwd_effective_gbs": round(by / (tot * 1e-3) / 1e9, 1),
+                  "fwd_bwd_frac_of_hbm_roof": round(by / (tot * 1e-3) / 1e9 / peaks()[0], 4)}
+        del Gd, dB, dA
+
     # ---- comparators on the same GPU (single-GPU only; informational) ------------------------------------
     comp = {}
     if world == 1 and not args.no_comparators:
@@ -510,6 +531,8 @@ def run_ours(args):
         "wall_ms_per_step": round(wall_ms / args.steps, 5),
         "comparators": comp,
     }
+    if phases is not None:
+        out["phases"] = phases
     if gathered_ms is not None:
         out["gathered"] = {"value": round(flops(w) / (gathered_ms * 1e-3) / 1e9, 2), "unit": "GFLOP/s",
                            "ms_per_step": round(gathered_ms, 5),
