@@ -107,3 +107,23 @@ def test_shard_rows_balances_nnz():
         assert per.max() <= rp[-1] / parts + lens.max()
     b = capi.shard_rows(rp, 4, 0.0, 1.0)      # rows only
     assert np.all(np.abs(np.diff(b) - len(lens) / 4) <= 1)
+
+
+def test_new_entry_points_validate_arguments_without_a_device():
+    L = capi.lib()
+    assert L.b200_plan_forward_host(None, None, 8, None, 0) == capi.ERR_INVALID
+    assert b"null plan" in L.b200_last_error()
+    assert L.b200_plan_forward_peers(None, None, 8, 8, None, 8, None, 0, None, None) == capi.ERR_INVALID
+    assert L.b200_csr_block_diag_cols(None, None, 10, 3, 4, None) == capi.ERR_INVALID      # rows % M != 0
+    assert L.b200_csr_block_diag_cols(None, None, 2**30, 1, 4, None) == capi.ERR_INVALID   # L * K overflows int32
+    assert L.b200_csr_block_diag_cols(None, None, 0, 3, 4, None) == capi.OK
+
+
+def test_task_size_rule_is_reflected_in_the_workspace_size():
+    L = capi.lib()
+    big = L.b200_spmm_workspace_bytes(1 << 20, 16 << 20, 128)      # 256-item tasks
+    small = L.b200_spmm_workspace_bytes(1000, 5000, 128)           # 32-item tasks: more tasks per item
+    assert big / ((1 << 20) + (16 << 20)) < small / 6000
+    capi.set_option("items_per_task", 512)
+    assert L.b200_spmm_workspace_bytes(1 << 20, 16 << 20, 128) < big
+    capi.set_option("items_per_task", 0)
