@@ -150,6 +150,19 @@ __device__ __forceinline__ void multimem_st(float* p, float a) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
+// Same bulk copy with an L2 evict-first hint: the col/val stream is read exactly once, it should not push the
+// re-used B rows out of L2.
+__device__ __forceinline__ void tma_bulk_g2s_stream(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                    uint64_t* bar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 // read-only 128/64/32-bit loads of B (gathered rows; keep in L1/L2)
 template <int VEC>
 struct Vec;

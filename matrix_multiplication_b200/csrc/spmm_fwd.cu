@@ -275,8 +275,8 @@ spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, 
   const int n_bulk = TMA ? ((je - a0) & ~3) : 0;
   if (TMA && tid == 0 && n_bulk > 0) {
     mbar_expect_tx(bar, (uint32_t)n_bulk * 8u);
-    tma_bulk_g2s(s_col, p.col + a0, (uint32_t)n_bulk * 4u, bar);
-    tma_bulk_g2s(s_val, p.val + a0, (uint32_t)n_bulk * 4u, bar);
+    tma_bulk_g2s_stream(s_col, p.col + a0, (uint32_t)n_bulk * 4u, bar);
+    tma_bulk_g2s_stream(s_val, p.val + a0, (uint32_t)n_bulk * 4u, bar);
   }
   for (int q = a0 + n_bulk + tid; q < je; q += blockDim.x) {  // fringe (or everything when !TMA)
     s_col[q - a0] = __ldg(p.col + q);
