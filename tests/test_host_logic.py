@@ -127,3 +127,22 @@ def test_task_size_rule_is_reflected_in_the_workspace_size():
     capi.set_option("items_per_task", 512)
     assert L.b200_spmm_workspace_bytes(1 << 20, 16 << 20, 128) < big
     capi.set_option("items_per_task", 0)
+
+
+def test_python_surface_has_the_reference_names():
+    """The 16 pybind entry points of the reference's custom_mm (src/custom_mm.cpp:393-416) and the public names
+    of its matmuls.py — importable without a GPU (calling them needs one)."""
+    import custom_mm
+    import matmuls
+    for name in ["init_cublas", "destroy_cublas", "init_cusparse", "destroy_cusparse", "cublas_mmul", "cublas_bmm",
+                 "cusparse_mmul", "dummy_kernel", "naive_spmm", "tiledspmm_inspect_csr", "tiledspmm_inspect_coo",
+                 "tiledspmm_mm", "tiledspmm_clean", "cusparse_inspect", "cusparse_mmul_opt", "cusparse_clean"]:
+        assert callable(getattr(custom_mm, name)), name
+    for name in ["custom_matmul", "cublasMM", "cublasTransaMM", "cublasTransbMM", "cublasTransabMM",
+                 "get_sparse_tensor_properties", "sparse_matmul", "cusparseMM", "naive_matmul", "naiveSpMM"]:
+        assert hasattr(matmuls, name), name
+    import inspect
+    assert list(inspect.signature(matmuls.sparse_matmul).parameters) == ["a", "b", "mm_op"]
+    assert list(inspect.signature(matmuls.custom_matmul).parameters) == ["a", "b", "mm_op", "bmm_op", "transa", "transb"]
+    assert matmuls.sparse_matmul.__defaults__[0] is custom_mm.cusparse_mmul      # the mm_op plug-in seam
+    assert matmuls.naive_matmul.__defaults__[0] is custom_mm.naive_spmm
