@@ -68,7 +68,9 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  * stage_mode: 0 = col/val read straight from global memory,
  *             1 = col/val segments staged in shared memory with TMA bulk copies
  *                 (cp.async.bulk + mbarrier); default 1.
- * items_per_task: merge-path items (row ends + non-zeros) per warp task; 0 = auto. */
+ * items_per_task: merge-path items (row ends + non-zeros) per warp task; 0 = auto (256, less for small problems).
+ * pipeline      : forward kernel variant, 0 = shipped (profiles/r1_variant_sweep.md lists the alternatives).
+ * flat_min_n    : smallest N served by the one-lane-group kernel (default 24; below it lane groups share a warp). */
 int b200_set_option(const char* name, int64_t value);
 int64_t b200_get_option(const char* name);
 

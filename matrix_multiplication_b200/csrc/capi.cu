@@ -216,7 +216,6 @@ int b200_set_option(const char* name, int64_t value) {
   B200_REQUIRE(name != nullptr, "option name");
   if (!strcmp(name, "stage_mode")) { options().stage_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
-  if (!strcmp(name, "batch")) { options().batch = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
@@ -226,7 +225,6 @@ int64_t b200_get_option(const char* name) {
   if (!name) return -1;
   if (!strcmp(name, "stage_mode")) return options().stage_mode;
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
-  if (!strcmp(name, "batch")) return options().batch;
   if (!strcmp(name, "pipeline")) return options().pipeline;
   if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
   return -1;

@@ -49,9 +49,9 @@ extern std::atomic<uint64_t> g_launches;
 struct Options {
   int stage_mode = 1;      // 1: TMA bulk staging of col/val, 0: direct global loads
   int items_per_task = 0;  // 0 = auto
-  int batch = 0;           // reserved
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
-  int pipeline = 0;        // flat kernel variant (0 = default; 1..3 = alternatives kept for profiling)
+  int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
+                           // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
 };
 Options& options();
 

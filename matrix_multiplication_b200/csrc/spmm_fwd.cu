@@ -354,9 +354,6 @@ spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, 
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   };
 
-  // Software pipeline, two chunks deep: the gathers of chunk i+1 are issued before the FMAs of
-  // chunk i, so a warp always has 8..16 B-row loads in flight (bytes in flight, not occupancy, is
-  // what feeds the L1 data path here).
   // A chunk in flight holds only its 8 gathered B slabs (the values are re-read from shared memory
   // when they are consumed), so nearly every live register is a load destination.
   struct Chunk {
