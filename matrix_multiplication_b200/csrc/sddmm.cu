@@ -32,7 +32,7 @@ sddmm_partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, i
 }
 
 template <int VEC, bool TMA, bool MULTI>
-__global__ void __launch_bounds__(SD_NW * 32, MULTI ? 3 : 5)
+__global__ void __launch_bounds__(SD_NW * 32, MULTI ? 3 : 8)
 sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int nnz,
              const float* __restrict__ G, unsigned ldg, const float* __restrict__ B, unsigned ldb, int N,
              float* __restrict__ out, const Boundary* __restrict__ bnd, int W, int n_tasks) {
@@ -89,17 +89,15 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
     const int off = c0 - a0;
     const int4 ca = *reinterpret_cast<const int4*>(s_col + off);
     const int4 cb = *reinterpret_cast<const int4*>(s_col + off + 4);
-    const int4 ra = *reinterpret_cast<const int4*>(s_row + off);
-    const int4 rb = *reinterpret_cast<const int4*>(s_row + off + 4);
     const int c[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-    const int r[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    const int r0 = s_row[off], r7 = s_row[off + 7];  // rows of the first / last position (garbage outside vm)
     const int lo = max(j0 - c0, 0), hi = min(j1 - c0, 8);
     const unsigned vm = ((1u << hi) - 1u) & ~((1u << lo) - 1u);  // positions of this task
     float d[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) d[k] = 0.f;
 
-    const bool one_row = vm == 0xffu && r[0] == r[7];  // rows are sorted: the whole chunk is in one row
+    const bool one_row = vm == 0xffu && r0 == r7;  // rows are sorted: the whole chunk is in one row
     if (MULTI && one_row) {
       // wide N: walk the slabs two deep — the gathers of slab s+1 are in flight while slab s is consumed
       auto load_slab = [&](int s, Vec<VEC>(&b)[8], Vec<VEC>& g) {
@@ -108,7 +106,7 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
         const int cc = active ? col0 : 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) b[k].load(B + (unsigned long long)(unsigned)c[k] * ldb + cc);
-        g.load(G + (unsigned long long)(unsigned)r[0] * ldg + cc);
+        g.load(G + (unsigned long long)(unsigned)r0 * ldg + cc);
         if (!active) {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) g.v[v] = 0.f;
@@ -138,43 +136,49 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
       if (one_row) {  // one G slab serves all 8 non-zeros (kept in registers across chunks when N fits one slab)
 #pragma unroll
         for (int k = 0; k < 8; ++k) b[k].load(B + (unsigned long long)(unsigned)c[k] * ldb + cc);
-        if (n_slabs > 1 || r[0] != cur_row) {
-          gcur.load(G + (unsigned long long)(unsigned)r[0] * ldg + cc);
+        if (n_slabs > 1 || r0 != cur_row) {
+          gcur.load(G + (unsigned long long)(unsigned)r0 * ldg + cc);
           if (!active) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) gcur.v[v] = 0.f;
           }
-          cur_row = r[0];
+          cur_row = r0;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
 #pragma unroll
           for (int v = 0; v < VEC; ++v) d[k] = fmaf(gcur.v[v], b[k].v[v], d[k]);
-      } else {  // mixed chunk (row ends inside it, or a task edge): one G gather per non-zero
-        Vec<VEC> g[8];
+      } else {  // mixed chunk (row ends inside it, or a task edge): one G gather per non-zero, in two halves
+        // of 4 so that only 4 B slabs + 4 G slabs are live at a time (register budget = occupancy here)
+        Vec<VEC> g4[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if ((vm >> k) & 1u) {
-            b[k].load(B + (unsigned long long)(unsigned)c[k] * ldb + cc);
-            g[k].load(G + (unsigned long long)(unsigned)r[k] * ldg + cc);
-          } else {
+        for (int h = 0; h < 2; ++h) {
+          Vec<VEC> b4[4];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { b[k].v[v] = 0.f; g[k].v[v] = 0.f; }
+          for (int k = 0; k < 4; ++k) {
+            const int kk = 4 * h + k;
+            if ((vm >> kk) & 1u) {
+              b4[k].load(B + (unsigned long long)(unsigned)c[kk] * ldb + cc);
+              g4[k].load(G + (unsigned long long)(unsigned)s_row[off + kk] * ldg + cc);
+            } else {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) { b4[k].v[v] = 0.f; g4[k].v[v] = 0.f; }
+            }
           }
+          if (!active) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) g4[k].v[v] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) d[4 * h + k] = fmaf(g4[k].v[v], b4[k].v[v], d[4 * h + k]);
         }
-        if (!active) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) g[k].v[v] = 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) d[k] = fmaf(g[k].v[v], b[k].v[v], d[k]);
         if (n_slabs == 1 && ((vm >> 7) & 1u)) {
-          cur_row = r[7];
-          gcur = g[7];
+          cur_row = r7;
+          gcur = g4[3];
         } else {
           cur_row = -1;
         }
