@@ -146,7 +146,8 @@ int b200_csr_block_diag_cols(const int32_t* d_row_ptr, int32_t* d_col_ind, int64
 
 /* ---- plans: the inspect / execute / clean triple -------------------------------
  * A plan borrows a device CSR, owns its scratch, and lazily builds + caches the
- * transposed CSR used by backward_B.  Not thread-safe per plan. */
+ * transposed CSR used by backward_B.  Not thread-safe per plan.  A plan belongs to the device that was current
+ * when it was created: calls made with another current device return B200_ERR_INVALID. */
 typedef struct b200_plan b200_plan;
 
 int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const float* d_val,

@@ -86,6 +86,7 @@ struct b200_plan {
   const float* val;
   int M, K, nnz;
   int max_row, empty_rows;
+  int device = 0;  // the device that was current at creation: every later call must run on it
   // cached transposed CSR (owned)
   int* t_row_ptr = nullptr;
   int* t_col = nullptr;
@@ -129,6 +130,16 @@ static int plan_ensure_bounds(b200_plan* p, int side, const int* row_ptr, int M,
   if (rc != B200_OK) return rc;
   p->pick[side] = k;
   p->bnd_valid[side] = true;
+  return B200_OK;
+}
+
+static int plan_check_device(const b200_plan* p) {
+  int dev = -1;
+  B200_CUDA_OK(cudaGetDevice(&dev));
+  if (dev != p->device) {
+    set_error("plan was created on device %d but the current device is %d", p->device, dev);
+    return B200_ERR_INVALID;
+  }
   return B200_OK;
 }
 
@@ -373,6 +384,7 @@ int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const f
   if (!p) { set_error("out of host memory"); return B200_ERR_ALLOC; }
   p->row_ptr = d_row_ptr; p->col = d_col_ind; p->val = d_val;
   p->M = (int)M; p->K = (int)K; p->nnz = (int)nnz;
+  if (cudaGetDevice(&p->device) != cudaSuccess) { cudaGetLastError(); p->device = 0; }
   cudaStream_t s = (cudaStream_t)stream;
   int* d_stats = nullptr;
   int h_stats[2] = {0, 0};
@@ -426,7 +438,9 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
   B200_REQUIRE(ldb < 0x7fffffffLL && ldc < 0x7fffffffLL, "leading dimension out of range");
   if (M == 0 || N == 0) return B200_OK;
   B200_REQUIRE(d_C != nullptr && (p->nnz == 0 || d_B != nullptr), "null B / C");
-  int rc = plan_ensure_bounds(p, side, row_ptr, M, max_row, N, s);
+  int rc = plan_check_device(p);
+  if (rc) return rc;
+  rc = plan_ensure_bounds(p, side, row_ptr, M, max_row, N, s);
   if (rc) return rc;
   rc = plan_ensure_ws(p, fwd_workspace_bytes(M, p->nnz, N));  // exact for this side (the task size depends on M + nnz)
   if (rc) return rc;
@@ -534,6 +548,8 @@ int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const floa
   if (p->nnz == 0 || p->M == 0) return B200_OK;
   B200_REQUIRE(d_dval != nullptr && (N == 0 || (d_G && d_B)), "null G / B / output");
   cudaStream_t s = (cudaStream_t)stream;
+  int rc_dev = plan_check_device(p);
+  if (rc_dev) return rc_dev;
   if (p->sd_bnd == nullptr) {
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->sd_bnd), sddmm_bounds_bytes(p->M, p->nnz)));
     int rc = launch_sddmm_partition(p->row_ptr, p->M, p->nnz, p->sd_bnd, s);
