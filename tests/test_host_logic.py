@@ -146,3 +146,36 @@ def test_python_surface_has_the_reference_names():
     assert list(inspect.signature(matmuls.custom_matmul).parameters) == ["a", "b", "mm_op", "bmm_op", "transa", "transb"]
     assert matmuls.sparse_matmul.__defaults__[0] is custom_mm.cusparse_mmul      # the mm_op plug-in seam
     assert matmuls.naive_matmul.__defaults__[0] is custom_mm.naive_spmm
+
+
+@pytest.mark.parametrize("W,NW", [(8, 4), (32, 4), (32, 1), (64, 8), (256, 4)])
+def test_flat_kernel_decomposition_matches_oracle(W, NW):
+    """The flat kernel's bookkeeping (chunk masks, task-edge masks, empty-row fill, head / tail pieces, fix list)
+    modelled in numpy on the library's own boundary function: every row written exactly once, product exact."""
+    from taskwalk_sim import simulate_flat
+    rng = np.random.default_rng(W * 10 + NW)
+    M, K, N = 150, 900, 3
+    rp, ci, va, _ = random_csr(rng, M, K, 0.012, heavy_rows=(0, 17, 18, 77, 149), empty_rows=(1, 2, 3, 60, 148))
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    C, written, n_fix = simulate_flat(rp, ci, va, (M, K), B, W, NW)
+    assert np.all(written == 1), np.where(written != 1)
+    assert oracle.rel_err(C, oracle.spmm_f64(rp, ci, va, (M, K), B)) <= 1e-12
+    if W < 900:
+        assert n_fix >= 5      # the five full rows are split
+
+
+def test_flat_kernel_decomposition_edge_shapes():
+    from taskwalk_sim import simulate_flat
+    rng = np.random.default_rng(3)
+    for lens in ([0, 0, 0, 5, 0], [40], [1] * 30, [0] * 9 + [100] + [0] * 9, [7, 8, 9, 16, 24, 0, 1], [3, 20, 0, 0, 13, 1]):
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(rp[-1])
+        ci = rng.integers(0, 11, nnz).astype(np.int32)
+        va = rng.standard_normal(nnz).astype(np.float32)
+        B = rng.standard_normal((11, 2)).astype(np.float32)
+        ref = oracle.spmm_f64(rp, ci, va, (len(lens), 11), B)
+        for W in (1, 2, 5, 8, 9, 16, 33):
+            for NW in (1, 4):
+                C, written, _ = simulate_flat(rp, ci, va, (len(lens), 11), B, W, NW)
+                assert np.all(written == 1), (lens, W, NW, written)
+                assert oracle.rel_err(C, ref) <= 1e-12, (lens, W, NW)
