@@ -127,6 +127,84 @@ fill_kernel(const float* __restrict__ dense, int M, int K, long long ld,
   }
 }
 
+// 128-bit variant of the fill: lane l owns columns 4l .. 4l+3 of every 128-column chunk.  Output order is
+// by column, i.e. lane-major: slot = base + (kept in lanes < l) + (kept before j within the lane).  The
+// cross-lane prefix comes from four ballots ("lane keeps >= k elements") instead of a shuffle scan.
+// Rows that keep more than a quarter of their elements take the one-element-per-lane path instead (their
+// time goes into the stores, which that path coalesces perfectly).
+__global__ void __launch_bounds__(256)
+fill_kernel_v4(const float* __restrict__ dense, int M, int K, long long ld,
+               const int* __restrict__ row_ptr, int* __restrict__ col, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  const int K4 = K >> 2;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M; row += warps_per_grid) {
+    const float* r = dense + (long long)row * ld;
+    int base = __ldg(row_ptr + row);
+    const int end = __ldg(row_ptr + row + 1);
+    if (base == end) continue;
+    if ((long long)(end - base) * 4 > K) {
+      // dense row (> 25 % kept): the stores dominate; one element per lane keeps them perfectly coalesced
+      for (int c0 = 0; c0 < K; c0 += 128) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * 32 + lane;
+          x[u] = (c < K) ? __ldcs(r + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool k = keep(x[u]);
+          const unsigned ball = __ballot_sync(FULL, k);
+          if (k) {
+            const int pos = base + __popc(ball & lt);
+            col[pos] = c0 + u * 32 + lane;
+            val[pos] = x[u];
+          }
+          base += __popc(ball);
+        }
+      }
+      continue;
+    }
+    const float4* r4 = reinterpret_cast<const float4*>(r);
+    for (int c4 = 0; c4 < K4; c4 += 64) {  // two 128-column chunks per iteration: two loads in flight per lane
+      float4 x[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = c4 + u * 32 + lane;
+        x[u] = (i < K4) ? __ldcs(r4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float e[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+        const bool k0 = keep(e[0]), k1 = keep(e[1]), k2 = keep(e[2]), k3 = keep(e[3]);
+        const int cnt = (int)k0 + (int)k1 + (int)k2 + (int)k3;
+        const unsigned b1 = __ballot_sync(FULL, cnt >= 1), b2 = __ballot_sync(FULL, cnt >= 2);
+        const unsigned b3 = __ballot_sync(FULL, cnt >= 3), b4 = __ballot_sync(FULL, cnt >= 4);
+        int pos = base + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt) + __popc(b4 & lt);
+        const int c0 = (c4 + u * 32 + lane) << 2;
+        if (k0) { col[pos] = c0;     val[pos] = e[0]; ++pos; }
+        if (k1) { col[pos] = c0 + 1; val[pos] = e[1]; ++pos; }
+        if (k2) { col[pos] = c0 + 2; val[pos] = e[2]; ++pos; }
+        if (k3) { col[pos] = c0 + 3; val[pos] = e[3]; }
+        base += __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4);
+      }
+    }
+    // K not a multiple of 4: the last 1-3 columns
+    for (int c = (K4 << 2) + lane; c < K; c += 32) {  // at most one iteration, lanes 0..2
+      const float xv = __ldcs(r + c);
+      const bool k = keep(xv);
+      const unsigned ball = __ballot_sync(__activemask(), k);
+      if (k) {
+        const int pos = base + __popc(ball & lt);
+        col[pos] = c;
+        val[pos] = xv;
+      }
+    }
+  }
+}
+
 __global__ void row_stats_kernel(const int* __restrict__ row_ptr, int M, int* __restrict__ out2) {
   int mx = 0, empty = 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
@@ -183,7 +261,9 @@ int launch_dense_count(const float* dense, int M, int K, long long ld, int* row_
 int launch_dense_fill(const float* dense, int M, int K, long long ld, const int* row_ptr, int* col,
                       float* val, cudaStream_t s) {
   if (M == 0 || K == 0) return B200_OK;
-  fill_kernel<<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr, col, val);
+  const bool v4 = (reinterpret_cast<uintptr_t>(dense) % 16 == 0) && (ld % 4 == 0) && K >= 4;
+  if (v4) fill_kernel_v4<<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr, col, val);
+  else fill_kernel<<<warp_grid(M), 256, 0, s>>>(dense, M, K, ld, row_ptr, col, val);
   B200_LAUNCH_OK("dense_fill_kernel");
   return B200_OK;
 }

@@ -251,3 +251,19 @@ def test_batched_product_is_one_launch(mods):
     ones = torch.ones_like(expected).double()
     assert torch.allclose(b2.grad.double(), a.double().transpose(-1, -2) @ ones, rtol=1e-4, atol=1e-4)
     assert torch.allclose(a2.grad.double(), ones @ b.double().transpose(-1, -2), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("K,ld", [(130, 132), (129, 132), (131, 256), (4, 8), (5, 8), (1000, 1024), (4096, 4096)])
+def test_dense_to_csr_strided_and_ragged_widths(mods, K, ld):
+    """The 128-bit fill path (ld % 4 == 0) with K not a multiple of 4 / of 128, on a strided view."""
+    torch, custom_mm, _ = mods
+    torch.manual_seed(K)
+    big = torch.randn(300, ld, device="cuda") * (torch.rand(300, ld, device="cuda") < 0.3)
+    big[7] = 0                      # an empty row
+    big[9] = 1.5                    # a full row
+    d = big[:, :K]
+    crow, col, val = custom_mm.dense_to_csr(d)
+    t = d.contiguous().to_sparse_csr()
+    assert torch.equal(crow.long(), t.crow_indices())
+    assert torch.equal(col.long(), t.col_indices())
+    assert torch.equal(val.view(torch.int32), t.values().view(torch.int32))
