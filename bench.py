@@ -30,7 +30,12 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+import warnings  # noqa: E402
+
 import numpy as np  # noqa: E402
+
+warnings.filterwarnings("ignore", message="Sparse CSR tensor support is in beta state")
+warnings.filterwarnings("ignore", message="Sparse invariant checks are implicitly disabled")
 
 
 def log(*a):
