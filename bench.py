@@ -564,7 +564,7 @@ def run_reference(args):
     M, K = w["shape"]
     N, nnz = w["N"], len(w["val"])
     base = {"impl": "reference", "metric": "CSR SpMM forward GFLOP/s (2*nnz*N)", "unit": "GFLOP/s",
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "n_gpus": args.gpus, "gpus_used": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "M": M, "K": K, "N": N, "nnz": nnz}}
     cpu = cpu_baseline(w)
