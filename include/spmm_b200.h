@@ -70,7 +70,11 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  *                 (cp.async.bulk + mbarrier); default 1.
  * items_per_task: merge-path items (row ends + non-zeros) per warp task; 0 = auto (256, less for small problems).
  * pipeline      : forward kernel variant, 0 = shipped (profiles/r1_variant_sweep.md lists the alternatives).
- * flat_min_n    : smallest N served by the one-lane-group kernel (default 24; below it lane groups share a warp). */
+ * flat_min_n    : smallest N served by the one-lane-group kernel (default 24; below it lane groups share a warp).
+ * tc_mode       : block-dense tensor-core path: 0 never, 1 auto (default), 2 whenever the shape allows it.
+ * tc_min_density_pct : auto rule threshold, nnz / (M*K) in percent (default 4).
+ * tc_nt, tc_terms, tc_split_acc : tile width override, which split-precision products are issued (bit mask, 7 = all),
+ *                 separate TMEM accumulator for the correction terms (accuracy studies). */
 int b200_set_option(const char* name, int64_t value);
 int64_t b200_get_option(const char* name);
 
@@ -172,6 +176,39 @@ int b200_plan_forward(b200_plan* plan, const float* d_B, int64_t ldb, int64_t N,
 int b200_plan_forward_peers(b200_plan* plan, const float* d_B, int64_t ldb, int64_t N,
                             float* d_C, int64_t ldc, float* const* peer_C, int n_peers, float* mc_C,
                             void* stream);
+/* ---- extended forward: block-dense tensor-core tiles, fused epilogue, transposed operands ---------------------
+ * Same product as b200_plan_forward with the options a sparse FC layer needs (the caller being replaced is
+ * benchmarks/cusparse_fc_layer.py:41-46: `cusparseMM.apply(inp, weight.t()) + bias`, which pays two transposes
+ * and a separate bias add per call):
+ *   B200_OP_B_TRANSPOSED : d_B is B^T, row-major [N, K] with leading dimension ldb (activations [tokens, features]);
+ *   B200_OP_C_TRANSPOSED : the result is written as C^T, row-major [N, M] with leading dimension ldc;
+ *   B200_OP_RELU         : max(x, 0) applied in the epilogue;
+ *   d_bias               : optional [M] vector added to every column of C (NULL = none);
+ *   B200_OP_NO_TC / B200_OP_FORCE_TC : override the path choice below.
+ * Path choice (also applied by b200_plan_forward / b200_plan_backward_B): when the operand is dense enough
+ * (option tc_min_density_pct, default 4 % of M*K) and N >= 32, the plan densifies the non-empty 128 x 32 tiles of
+ * A once (fp32 split into tf32 hi + lo) and the product runs on the tensor cores (tcgen05.mma kind::tf32, three
+ * products per k-step, fp32 accumulation in TMEM): fp32-grade accuracy (rel-err <= 1e-5 vs fp64 is tested), 2-6x the
+ * gather kernels' throughput.  This replaces the reference's cuSPARSE call for dense-ish operands
+ * (src/baseline_mm.cu:186-213) and is what its dense comparison path (src/baseline_mm.cu:52-102) is measured against.
+ * Inf/NaN in the dense operand are detected on the device and that call runs on the CSR order instead (a dense
+ * contraction would turn 0 * Inf into NaN).  Otherwise the gather kernels run. */
+#define B200_OP_B_TRANSPOSED 1u
+#define B200_OP_C_TRANSPOSED 2u
+#define B200_OP_RELU 4u
+#define B200_OP_NO_TC 8u
+#define B200_OP_FORCE_TC 16u
+int b200_plan_forward_ex(b200_plan* plan, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
+                         const float* d_bias, uint32_t flags, void* stream);
+/* grad_B = A^T * G with the same operand options (d_G may be G^T [N, M], d_dB may be written as dB^T [N, K]). */
+int b200_plan_backward_B_ex(b200_plan* plan, const float* d_G, int64_t ldg, int64_t N, float* d_dB, int64_t lddb,
+                            uint32_t flags, void* stream);
+/* Block-dense state of a plan side (0 = A, 1 = A^T): stored tiles, their bytes, and the path the last product took
+ * (0 gather kernels, 1 tensor-core tiles, 2 strided fallback). */
+int b200_plan_tc_info(const b200_plan* plan, int side, int64_t* n_tiles, int64_t* tile_bytes, int* last_path);
+/* Debug aid: non-zero when a pipeline wait of the last tensor-core launch gave up (protocol bug); synchronises. */
+int b200_tc_last_timeout(const b200_plan* plan, int* code);
+
 /* grad_B[K,N] = A^T * G[M,N]  — SpMM over the cached transposed CSR (matmuls.py:253). */
 int b200_plan_backward_B(b200_plan* plan, const float* d_G, int64_t ldg, int64_t N,
                          float* d_dB, int64_t lddb, void* stream);

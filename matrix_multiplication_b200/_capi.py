@@ -18,6 +18,7 @@ HEADER = PKG.parent / "include" / "spmm_b200.h"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = range(5)
 FLAG_NO_STAGE = 1
+OP_B_TRANSPOSED, OP_C_TRANSPOSED, OP_RELU, OP_NO_TC, OP_FORCE_TC = 1, 2, 4, 8, 16
 
 
 class B200Error(RuntimeError):
@@ -64,6 +65,10 @@ SIGNATURES = {
     "b200_plan_forward": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b200_plan_forward_host": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int]),
     "b200_plan_forward_peers": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "b200_plan_forward_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, C.c_uint32, _vp]),
+    "b200_plan_backward_B_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.c_uint32, _vp]),
+    "b200_plan_tc_info": (C.c_int, [_vp, C.c_int, _i64p, _i64p, C.POINTER(C.c_int)]),
+    "b200_tc_last_timeout": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "b200_plan_backward_B": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b200_plan_backward_A": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
     "b200_spmm_csr_forward_host": (C.c_int, [_i32p, _i32p, _f32p, _i64, _i64, _i64, _f32p, _i64, _f32p]),
@@ -264,6 +269,30 @@ class Plan:
         N = B.shape[1]
         check(lib().b200_plan_forward(self._h, _dp(B), N, N, _dp(Cout), N, C.c_void_p(stream)))
         return Cout
+
+    def forward_ex(self, B, Cout, bias=None, flags=0, stream=0):
+        """Extended forward: B is [K, N] (or [N, K] with OP_B_TRANSPOSED), Cout [M, N] (or [N, M] with
+        OP_C_TRANSPOSED); bias [M] and ReLU are fused into the epilogue."""
+        N = B.shape[0] if flags & OP_B_TRANSPOSED else B.shape[1]
+        check(lib().b200_plan_forward_ex(self._h, _dp(B), B.stride(0), N, _dp(Cout), Cout.stride(0), _dp(bias),
+                                         flags, C.c_void_p(stream)))
+        return Cout
+
+    def backward_B_ex(self, G, dB, flags=0, stream=0):
+        N = G.shape[0] if flags & OP_B_TRANSPOSED else G.shape[1]
+        check(lib().b200_plan_backward_B_ex(self._h, _dp(G), G.stride(0), N, _dp(dB), dB.stride(0), flags,
+                                            C.c_void_p(stream)))
+        return dB
+
+    def tc_info(self, side=0):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int()
+        check(lib().b200_plan_tc_info(self._h, side, C.byref(a), C.byref(b), C.byref(c)))
+        return {"tiles": a.value, "bytes": b.value, "last_path": c.value}
+
+    def tc_timeout(self):
+        c = C.c_int()
+        check(lib().b200_tc_last_timeout(self._h, C.byref(c)))
+        return c.value
 
     def forward_host(self, B_host, C_host, panels=0):
         """End-to-end forward with (pinned) HOST buffers — numpy arrays or CPU torch tensors; uploads, the product

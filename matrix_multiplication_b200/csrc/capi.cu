@@ -109,6 +109,14 @@ struct b200_plan {
   cudaEvent_t hev[2][16] = {};
   PeerSet* d_peers = nullptr;  // device copy of the peer pointers of the multi-GPU epilogue
   PeerSet h_peers{};           // what d_peers currently holds
+  // block-dense tensor-core path: densified tiles of A (side 0) and A^T (side 1), built on first use
+  TcStore tc[2];
+  bool tc_built[2] = {false, false};
+  bool tc_failed[2] = {false, false};  // the build was refused (memory): do not retry on every call
+  bool tc_stale[2] = {false, false};   // values changed since the tiles were packed
+  void* tc_ws = nullptr;               // [non-finite flag | debug word | packed dense operand]
+  size_t tc_ws_bytes = 0;
+  int last_path = 0;                   // 0 gather kernels, 1 tensor-core tiles, 2 strided fallback
 };
 
 // Boundaries depend on (row_ptr, W, heavy) only: compute once per plan side, reuse for every N.
@@ -229,6 +237,14 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
+  if (!strcmp(name, "tc_mode")) { options().tc_mode = (int)value; return B200_OK; }
+  if (!strcmp(name, "tc_nt")) {
+    B200_REQUIRE(value == 0 || (value % 32 == 0 && value >= 32 && value <= 256), "tc_nt must be 0 or a multiple of 32 up to 256");
+    options().tc_nt = (int)value; return B200_OK;
+  }
+  if (!strcmp(name, "tc_terms")) { options().tc_terms = (int)value & 7; return B200_OK; }
+  if (!strcmp(name, "tc_split_acc")) { options().tc_split_acc = value ? 1 : 0; return B200_OK; }
+  if (!strcmp(name, "tc_min_density_pct")) { options().tc_min_density_pct = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
   return B200_ERR_INVALID;
 }
@@ -238,6 +254,11 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "pipeline")) return options().pipeline;
   if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
+  if (!strcmp(name, "tc_mode")) return options().tc_mode;
+  if (!strcmp(name, "tc_nt")) return options().tc_nt;
+  if (!strcmp(name, "tc_terms")) return options().tc_terms;
+  if (!strcmp(name, "tc_split_acc")) return options().tc_split_acc;
+  if (!strcmp(name, "tc_min_density_pct")) return options().tc_min_density_pct;
   return -1;
 }
 
@@ -409,7 +430,8 @@ int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
   cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd); cudaFree(p->d_peers);
-  cudaFree(p->hB); cudaFree(p->hC);
+  cudaFree(p->hB); cudaFree(p->hC); cudaFree(p->tc_ws);
+  tc_store_free(&p->tc[0]); tc_store_free(&p->tc[1]);
   for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
   for (int j = 0; j < 2; ++j) for (int i = 0; i < 16; ++i) if (p->hev[j][i]) cudaEventDestroy(p->hev[j][i]);
   cudaGetLastError();
@@ -420,6 +442,7 @@ int b200_plan_destroy(b200_plan* p) {
 int b200_plan_values_updated(b200_plan* p) {
   B200_REQUIRE(p != nullptr, "null plan");
   p->t_val_stale = true;
+  p->tc_stale[0] = p->tc_stale[1] = true;
   return B200_OK;
 }
 
@@ -465,11 +488,130 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
                              p->bnd_valid[side] ? &p->pick[side] : nullptr, s, d_peers);
 }
 
+// Should this product run on the block-dense tensor-core path?  ("crossover rule")
+static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t flags) {
+  if (flags & B200_OP_NO_TC) return false;
+  const int mode = options().tc_mode;
+  if (mode == 0 && !(flags & B200_OP_FORCE_TC)) return false;
+  if (M <= 0 || K <= 0 || p->nnz <= 0 || N <= 0) return false;
+  const int64_t MB = (M + 127) / 128, KT = (K + 31) / 32;
+  if (MB * KT > ((int64_t)1 << 26)) return false;
+  if (std::min<int64_t>(MB * KT, p->nnz) * 32768 > ((int64_t)24 << 30)) return false;  // densified tiles
+  if ((flags & B200_OP_FORCE_TC) || mode == 2) return true;
+  // auto: a dense-enough operand (every gathered B element feeds one FMA on the gather path, 128 on this one)
+  // and enough dense columns to fill a tile
+  const double density = (double)p->nnz / ((double)M * (double)K);
+  return N >= 32 && density * 100.0 >= (double)options().tc_min_density_pct;
+}
+
+static int plan_ensure_tc(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M,
+                          int K, cudaStream_t s) {
+  if (p->tc_failed[side]) return B200_ERR_ALLOC;
+  if (!p->tc_built[side]) {
+    int rc = tc_store_build(row_ptr, col, val, M, K, p->nnz, &p->tc[side], s);
+    if (rc != B200_OK) {
+      p->tc_failed[side] = true;
+      return rc;
+    }
+    p->tc_built[side] = true;
+    p->tc_stale[side] = false;
+  } else if (p->tc_stale[side]) {
+    int rc = tc_store_refresh(row_ptr, col, val, p->nnz, &p->tc[side], s);
+    if (rc != B200_OK) return rc;
+    p->tc_stale[side] = false;
+  }
+  return B200_OK;
+}
+
+// Extended product over one side of the plan (A or the cached A^T): optional transposed dense operand /
+// transposed result, bias per output row and ReLU fused into the epilogue, tensor-core tiles when the
+// operand is dense enough.
+static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M, int K,
+                        int max_row, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
+                        const float* d_bias, uint32_t flags, cudaStream_t s) {
+  const bool bt = (flags & B200_OP_B_TRANSPOSED) != 0, ct = (flags & B200_OP_C_TRANSPOSED) != 0;
+  const bool relu = (flags & B200_OP_RELU) != 0;
+  B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
+  B200_REQUIRE(ldb >= (bt ? K : N) && ldc >= (ct ? M : N), "leading dimension too small");
+  B200_REQUIRE(ldb < 0x7fffffffLL && ldc < 0x7fffffffLL, "leading dimension out of range");
+  if (M == 0 || N == 0) return B200_OK;
+  B200_REQUIRE(d_C != nullptr && (p->nnz == 0 || d_B != nullptr), "null B / C");
+  int rc = plan_check_device(p);
+  if (rc) return rc;
+  if (plan_wants_tc(p, M, K, N, flags)) {
+    rc = plan_ensure_tc(p, side, row_ptr, col, val, M, K, s);
+    if (rc == B200_OK) {
+      const int nt = options().tc_nt > 0 ? options().tc_nt : tc_pick_nt(p->tc[side].MB, (int)N, device_sm_count());
+      const size_t need = tc_pack_b_bytes(K, (int)N, nt);
+      if (p->tc_ws_bytes < need) {
+        if (p->tc_ws) { B200_CUDA_OK(cudaStreamSynchronize(s)); B200_CUDA_OK(cudaFree(p->tc_ws)); p->tc_ws = nullptr; p->tc_ws_bytes = 0; }
+        if (cudaMalloc(&p->tc_ws, need) != cudaSuccess) {
+          cudaGetLastError();
+          set_error("cudaMalloc of %zu bytes for the packed dense operand failed", need);
+          return B200_ERR_ALLOC;
+        }
+        p->tc_ws_bytes = need;
+      }
+      rc = launch_tc_forward(p->tc[side], d_B, ldb, (int)N, d_C, ldc, d_bias, flags, p->tc_ws, p->tc_ws_bytes, nt, s);
+      if (rc) return rc;
+      // stands in only when the packer saw Inf/NaN in the dense operand (device-side flag, no host sync)
+      rc = launch_spmm_strided(row_ptr, col, val, M, (int)N, d_B, bt ? 1 : ldb, bt ? ldb : 1, d_C, ct ? 1 : ldc,
+                               ct ? ldc : 1, d_bias, relu, reinterpret_cast<const int*>(p->tc_ws), s);
+      p->last_path = 1;
+      return rc;
+    }
+    if (flags & B200_OP_FORCE_TC) return rc;  // otherwise fall through to the gather kernels
+  }
+  if (bt || ct || relu || d_bias != nullptr) {
+    p->last_path = 2;
+    return launch_spmm_strided(row_ptr, col, val, M, (int)N, d_B, bt ? 1 : ldb, bt ? ldb : 1, d_C, ct ? 1 : ldc,
+                               ct ? ldc : 1, d_bias, relu, nullptr, s);
+  }
+  p->last_path = 0;
+  return plan_spmm(p, side, row_ptr, col, val, M, K, max_row, d_B, ldb, N, d_C, ldc, s);
+}
+
 int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
                       void* stream) {
   B200_REQUIRE(p != nullptr, "null plan");
-  return plan_spmm(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc,
-                   (cudaStream_t)stream);
+  return plan_spmm_ex(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc, nullptr, 0u,
+                      (cudaStream_t)stream);
+}
+
+int b200_plan_forward_ex(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
+                         const float* d_bias, uint32_t flags, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  return plan_spmm_ex(p, 0, p->row_ptr, p->col, p->val, p->M, p->K, p->max_row, d_B, ldb, N, d_C, ldc, d_bias,
+                      flags, (cudaStream_t)stream);
+}
+
+int b200_plan_backward_B_ex(b200_plan* p, const float* d_G, int64_t ldg, int64_t N, float* d_dB, int64_t lddb,
+                            uint32_t flags, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  B200_REQUIRE((flags & B200_OP_RELU) == 0, "ReLU is a forward epilogue");
+  int rc = plan_ensure_transpose(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return plan_spmm_ex(p, 1, p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->t_max_row, d_G, ldg, N, d_dB, lddb,
+                      nullptr, flags, (cudaStream_t)stream);
+}
+
+int b200_plan_tc_info(const b200_plan* p, int side, int64_t* n_tiles, int64_t* tile_bytes, int* last_path) {
+  B200_REQUIRE(p != nullptr && (side == 0 || side == 1), "null plan / bad side");
+  if (n_tiles) *n_tiles = p->tc_built[side] ? p->tc[side].n_tiles : 0;
+  if (tile_bytes) *tile_bytes = p->tc_built[side] ? (int64_t)p->tc[side].tile_bytes : 0;
+  if (last_path) *last_path = p->last_path;
+  return B200_OK;
+}
+
+int b200_tc_last_timeout(const b200_plan* p, int* code) {
+  B200_REQUIRE(p != nullptr && code != nullptr, "null plan / code");
+  *code = 0;
+  if (p->tc_ws != nullptr) {
+    int h[2] = {0, 0};
+    B200_CUDA_OK(cudaMemcpy(h, p->tc_ws, sizeof(h), cudaMemcpyDeviceToHost));
+    *code = h[1];
+  }
+  return B200_OK;
 }
 
 int b200_plan_forward_host(b200_plan* p, const float* h_B, int64_t N, float* h_C, int panels) {
@@ -536,8 +678,8 @@ int b200_plan_backward_B(b200_plan* p, const float* d_G, int64_t ldg, int64_t N,
   B200_REQUIRE(p != nullptr, "null plan");
   int rc = plan_ensure_transpose(p, (cudaStream_t)stream);
   if (rc) return rc;
-  return plan_spmm(p, 1, p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->t_max_row, d_G, ldg, N, d_dB, lddb,
-                   (cudaStream_t)stream);
+  return plan_spmm_ex(p, 1, p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->t_max_row, d_G, ldg, N, d_dB, lddb,
+                      nullptr, 0u, (cudaStream_t)stream);
 }
 
 int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,

@@ -52,6 +52,12 @@ struct Options {
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
   int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
                            // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
+  // block-dense tensor-core path (tc_gemm.cu)
+  int tc_mode = 1;         // 0 = never, 1 = auto (density / N rule), 2 = whenever the shape allows it
+  int tc_nt = 0;           // tile width override (multiple of 32, <= 256); 0 = auto
+  int tc_terms = 7;        // which split-precision products are issued: 1 hi*hi, 2 hi*lo, 4 lo*hi
+  int tc_split_acc = 0;    // 1 = correction terms accumulate in their own TMEM columns
+  int tc_min_density_pct = 4;  // auto rule: nnz / (M*K) at or above this percentage
 };
 Options& options();
 
@@ -267,6 +273,29 @@ int launch_dense_fill(const float* dense, int M, int K, long long ld, const int*
                       float* val, cudaStream_t s);
 int launch_row_stats(const int* row_ptr, int M, int* d_out2 /* max_len, empty */, cudaStream_t s);
 int launch_block_diag(const int* row_ptr, int* col, int rows, int M, int K, cudaStream_t s);
+
+// block-dense tensor-core path (tc_gemm.cu): the non-empty 128 x 32 tiles of a CSR matrix, densified
+struct TcStore {
+  int M = 0, K = 0, MB = 0, KT = 0, n_tiles = 0;
+  int* blk_ptr = nullptr;         // [MB + 1] first stored tile of every 128-row block
+  int* blk_kt = nullptr;          // [n_tiles] k-tile index of every stored tile
+  int* scan = nullptr;            // [MB * KT] slot of tile (mb, kt) (exclusive scan of the occupancy flags)
+  unsigned char* tiles = nullptr; // n_tiles x 32 KB (hi/lo swizzled atoms)
+  size_t tile_bytes = 0;
+};
+int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz, TcStore* st,
+                   cudaStream_t s);
+int tc_store_refresh(const int* row_ptr, const int* col, const float* val, int nnz, TcStore* st, cudaStream_t s);
+void tc_store_free(TcStore* st);
+int tc_pick_nt(int MB, int N, int sms);
+size_t tc_pack_b_bytes(int K, int N, int nt);
+int launch_tc_forward(const TcStore& st, const float* B, long long ldb, int N, float* C, long long ldc,
+                      const float* bias, unsigned flags, void* ws, size_t ws_bytes, int nt, cudaStream_t s);
+// generic strided CSR SpMM (any B / C strides, bias, ReLU): the correctness fallback of the extended forward;
+// skipped on the device when run_if != nullptr and *run_if == 0
+int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, int M, int N, const float* B,
+                        long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,
+                        const float* bias, bool relu, const int* run_if, cudaStream_t s);
 
 // per-device cached scratch (grown on demand; stream-ordered use only)
 int get_scratch(size_t bytes, void** ptr);
