@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """All BASELINE.json configs on one B200: forward SpMM, grad_B (SpMM over the cached transposed CSR),
-grad_A (SDDMM) and dense->CSR of the engine, next to cuSPARSE (`torch.sparse.mm`, CSR_ALG2 under the hood), the
-reference build's `cusparse_mmul` (oracle/_ref, when present) and the dense cuBLAS SGEMM on the densified A.
+grad_A (SDDMM) and dense->CSR of the engine, next to
+  * cuSPARSE, kernel-fair: cusparseSpMM CSR_ALG2 with descriptors / buffer / preprocess hoisted (tools/cusparse_fair.cu),
+  * cuSPARSE as torch calls it (`torch.sparse.mm`, descriptors per call) and as the reference build calls it
+    (`cusparse_mmul` of oracle/_ref, per-call cudaMalloc), when present,
+  * the dense crossover: cuBLAS SGEMM (fp32 SIMT), TF32 and BF16 tensor-core GEMMs on the densified A.
+Cold = L2 flushed before every timed launch; warm = back-to-back launches (operands L2-resident where they fit).
 
     python benchmarks/run_configs.py [--configs c1,c2,c3,c4,c5] [--out profiles/r1_configs.json]
 
@@ -22,6 +26,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from matrix_multiplication_b200 import capi, synthetic  # noqa: E402
+from tools import cusparse_fair  # noqa: E402
 
 PEAK = 6549.1
 try:
@@ -41,6 +46,19 @@ def timeit(fn, iters, flush):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return float(np.median(ts))
+
+
+def timeit_warm(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
 def configs(which):
@@ -114,12 +132,30 @@ def main():
         by_a = synthetic.sddmm_algorithmic_bytes(M, K, nnz, N)
         t = timeit(lambda: plan.forward(B, C, stream=stream), args.iters, flush)
         r["fwd_ms"], r["fwd_gflops"], r["fwd_gbs"], r["fwd_frac"] = t, fl / t / 1e6, by_f / t / 1e6, by_f / t / 1e6 / PEAK
+        r["fwd_path"] = ["gather", "tensor-core tiles", "strided"][plan.tc_info()["last_path"]]
+        r["fwd_warm_ms"] = timeit_warm(lambda: plan.forward(B, C, stream=stream), args.iters * 2)
+        if r["fwd_path"] != "gather":  # the gather kernels on the same operand, for the crossover table
+            from matrix_multiplication_b200._capi import OP_NO_TC
+            r["fwd_gather_ms"] = timeit(lambda: plan.forward_ex(B, C, flags=OP_NO_TC, stream=stream), args.iters, flush)
+            plan.forward(B, C, stream=stream)
         plan.backward_B(G, dB, stream=stream)  # builds + caches the transposed CSR (inspector time, not timed)
         t = timeit(lambda: plan.backward_B(G, dB, stream=stream), args.iters, flush)
         r["gradB_ms"], r["gradB_gbs"], r["gradB_frac"] = t, by_b / t / 1e6, by_b / t / 1e6 / PEAK
         t = timeit(lambda: plan.backward_A(G, B, dA, stream=stream), args.iters, flush)
         r["gradA_ms"], r["gradA_gbs"], r["gradA_frac"] = t, by_a / t / 1e6, by_a / t / 1e6 / PEAK
         # comparators
+        try:
+            Cf = torch.empty(M, N, device=dev)
+            fair = cusparse_fair.FairSpMM(crow, col, val, (M, K), B, Cf, stream=stream)
+            fair.run()
+            r["cusparse_fair_ms"] = timeit(fair.run, args.iters, flush)
+            r["cusparse_fair_warm_ms"] = timeit_warm(fair.run, args.iters * 2)
+            r["rel_diff_vs_cusparse_fair"] = float((Cf - C).abs().max() / Cf.abs().max().clamp_min(1e-30))
+            fair.close()
+            del Cf
+        except Exception as e:  # comparator only
+            r["cusparse_fair_ms"] = None
+            r["cusparse_fair_error"] = str(e)[:80]
         a_t = torch.sparse_csr_tensor(crow.long(), col.long(), val, size=(M, K))
         try:
             Cs = torch.sparse.mm(a_t, B)
@@ -138,13 +174,20 @@ def main():
                 r["ref_cusparse_mmul_ms"] = None
         if not args.no_dense and M * K <= (1 << 28):
             Ad = a_t.to_dense()
+            torch.backends.cuda.matmul.allow_tf32 = False
             r["cublas_sgemm_ms"] = timeit(lambda: torch.mm(Ad, B), max(3, args.iters // 2), flush)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            r["cublas_tf32_ms"] = timeit(lambda: torch.mm(Ad, B), max(3, args.iters // 2), flush)
+            torch.backends.cuda.matmul.allow_tf32 = False
+            Ah, Bh = Ad.bfloat16(), B.bfloat16()
+            r["cublas_bf16_ms"] = timeit(lambda: torch.mm(Ah, Bh), max(3, args.iters // 2), flush)
+            del Ah, Bh
             # dense -> CSR of the engine on the densified A (bit-exact check against the generator's CSR)
             import custom_mm
             crow2, col2, val2 = custom_mm.dense_to_csr(Ad)
             assert torch.equal(crow2, crow) and torch.equal(col2, col) and torch.equal(val2.view(torch.int32), val.view(torch.int32))
             t = timeit(lambda: custom_mm.dense_to_csr(Ad), max(3, args.iters // 2), flush)
-            by_d = 8.0 * M * K + 4.0 * (M + 1) + 8.0 * nnz
+            by_d = 4.0 * M * K + 4.0 * (M + 1) + 8.0 * nnz  # the dense matrix counted ONCE (algorithmic bytes)
             r["dense2csr_ms"], r["dense2csr_gbs"], r["dense2csr_frac"] = t, by_d / t / 1e6, by_d / t / 1e6 / PEAK
             t = timeit(lambda: Ad.to_sparse_csr(), max(3, args.iters // 2), flush)
             r["torch_to_sparse_csr_ms"] = t
@@ -158,12 +201,13 @@ def main():
 
     def f(x, d=3):
         return "—" if x is None else f"{x:.{d}f}"
-    print("\n| config | nnz | fwd ms | fwd GFLOP/s | fwd GB/s (of roof) | cuSPARSE ms | speed-up | cuBLAS SGEMM ms | grad_B ms (of roof) | grad_A ms (of roof) | dense→CSR ms (of roof) |")
-    print("|---|---|---|---|---|---|---|---|---|---|---|")
+    print("\n| config | nnz | path | fwd ms (warm) | fwd GFLOP/s | fwd GB/s (of roof) | cuSPARSE kernel-fair ms (warm) | speed-up | torch.sparse.mm ms | gather ms | SGEMM / TF32 / BF16 GEMM ms | grad_B ms (of roof) | grad_A ms (of roof) | dense→CSR ms (of roof) |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for r in rows:
-        su = (r["cusparse_ms"] / r["fwd_ms"]) if r.get("cusparse_ms") else None
-        print(f"| {r['config']} | {r['nnz']} | {f(r['fwd_ms'], 4)} | {r['fwd_gflops']:.0f} | {r['fwd_gbs']:.0f} ({100 * r['fwd_frac']:.1f} %) | "
-              f"{f(r.get('cusparse_ms'), 4)} | {f(su, 2)}× | {f(r.get('cublas_sgemm_ms'), 4)} | "
+        su = (r["cusparse_fair_ms"] / r["fwd_ms"]) if r.get("cusparse_fair_ms") else None
+        print(f"| {r['config']} | {r['nnz']} | {r.get('fwd_path', '')} | {f(r['fwd_ms'], 4)} ({f(r.get('fwd_warm_ms'), 4)}) | {r['fwd_gflops']:.0f} | {r['fwd_gbs']:.0f} ({100 * r['fwd_frac']:.1f} %) | "
+              f"{f(r.get('cusparse_fair_ms'), 4)} ({f(r.get('cusparse_fair_warm_ms'), 4)}) | {f(su, 2)}× | {f(r.get('cusparse_ms'), 4)} | {f(r.get('fwd_gather_ms'), 4)} | "
+              f"{f(r.get('cublas_sgemm_ms'), 4)} / {f(r.get('cublas_tf32_ms'), 4)} / {f(r.get('cublas_bf16_ms'), 4)} | "
               f"{f(r['gradB_ms'], 4)} ({100 * r['gradB_frac']:.1f} %) | {f(r['gradA_ms'], 4)} ({100 * r['gradA_frac']:.1f} %) | "
               + (f"{f(r['dense2csr_ms'], 4)} ({100 * r['dense2csr_frac']:.1f} %) |" if "dense2csr_ms" in r else "— |"))
 

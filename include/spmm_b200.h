@@ -73,8 +73,9 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  * flat_min_n    : smallest N served by the one-lane-group kernel (default 24; below it lane groups share a warp).
  * tc_mode       : block-dense tensor-core path: 0 never, 1 auto (default), 2 whenever the shape allows it.
  * tc_min_density_pct : auto rule threshold, nnz / (M*K) in percent (default 4).
- * tc_nt, tc_terms, tc_split_acc : tile width override, which split-precision products are issued (bit mask, 7 = all),
- *                 separate TMEM accumulator for the correction terms (accuracy studies). */
+ * tc_kind       : split-precision element kind: 0 = tf32 hi + lo, 1 = fp16 hi + lo with per-row / per-column scaling.
+ * tc_nt, tc_terms, tc_chunk : tile width override (multiple of 64), which split-precision products are issued (bit mask,
+ *                 7 = all), k-tiles accumulated in TMEM between two fp32 register accumulations (accuracy studies). */
 int b200_set_option(const char* name, int64_t value);
 int64_t b200_get_option(const char* name);
 
@@ -203,6 +204,10 @@ int b200_plan_forward_ex(b200_plan* plan, const float* d_B, int64_t ldb, int64_t
 /* grad_B = A^T * G with the same operand options (d_G may be G^T [N, M], d_dB may be written as dB^T [N, K]). */
 int b200_plan_backward_B_ex(b200_plan* plan, const float* d_G, int64_t ldg, int64_t N, float* d_dB, int64_t lddb,
                             uint32_t flags, void* stream);
+/* 1 if a product with N dense columns over this side of the plan (0 = A, 1 = A^T) would take the tensor-core tiles
+ * under the current options and flags, else 0.  Callers that hold their operands transposed use it to decide whether
+ * to pass them as they are (B200_OP_*_TRANSPOSED are served efficiently by the tiles only). */
+int b200_plan_would_use_tc(const b200_plan* plan, int side, int64_t N, uint32_t flags);
 /* Block-dense state of a plan side (0 = A, 1 = A^T): stored tiles, their bytes, and the path the last product took
  * (0 gather kernels, 1 tensor-core tiles, 2 strided fallback). */
 int b200_plan_tc_info(const b200_plan* plan, int side, int64_t* n_tiles, int64_t* tile_bytes, int* last_path);

@@ -19,6 +19,8 @@ HEADER = PKG.parent / "include" / "spmm_b200.h"
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = range(5)
 FLAG_NO_STAGE = 1
 OP_B_TRANSPOSED, OP_C_TRANSPOSED, OP_RELU, OP_NO_TC, OP_FORCE_TC = 1, 2, 4, 8, 16
+TC_KIND_TF32, TC_KIND_F16 = 0, 1
+TC_KIND_DEFAULT = TC_KIND_F16
 
 
 class B200Error(RuntimeError):
@@ -67,6 +69,7 @@ SIGNATURES = {
     "b200_plan_forward_peers": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), C.c_int, _vp, _vp]),
     "b200_plan_forward_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, C.c_uint32, _vp]),
     "b200_plan_backward_B_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.c_uint32, _vp]),
+    "b200_plan_would_use_tc": (C.c_int, [_vp, C.c_int, _i64, C.c_uint32]),
     "b200_plan_tc_info": (C.c_int, [_vp, C.c_int, _i64p, _i64p, C.POINTER(C.c_int)]),
     "b200_tc_last_timeout": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "b200_plan_backward_B": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
@@ -283,6 +286,9 @@ class Plan:
         check(lib().b200_plan_backward_B_ex(self._h, _dp(G), G.stride(0), N, _dp(dB), dB.stride(0), flags,
                                             C.c_void_p(stream)))
         return dB
+
+    def would_use_tc(self, N, side=0, flags=0):
+        return bool(lib().b200_plan_would_use_tc(self._h, side, N, flags))
 
     def tc_info(self, side=0):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int()

@@ -101,6 +101,8 @@ struct b200_plan {
   void* bnd[2] = {nullptr, nullptr};
   FwdPick pick[2];
   bool bnd_valid[2] = {false, false};
+  int* cnt[2] = {nullptr, nullptr};  // persistent arrival counters of split-row pieces (self-resetting)
+  size_t cnt_bytes[2] = {0, 0};
   int t_max_row = -1;
   Boundary* sd_bnd = nullptr;  // SDDMM task boundaries (heavy threshold 0)
   // host-buffer pipeline (b200_plan_forward_host): device B / C, three streams, per-panel events
@@ -178,6 +180,18 @@ static int plan_ensure_transpose(b200_plan* p, cudaStream_t s) {
     int rc = launch_transpose(p->row_ptr, p->col, p->val, p->M, p->K, p->nnz, p->t_row_ptr, p->t_col,
                               p->t_val, p->t_perm, s);
     if (rc != B200_OK) return rc;
+    // longest row of A^T: lets the backward side skip the piece machinery when no row can be split
+    int* d_stats = nullptr;
+    int h_stats[2] = {0, 0};
+    B200_CUDA_OK(cudaMalloc(&d_stats, 2 * sizeof(int)));
+    rc = launch_row_stats(p->t_row_ptr, p->K, d_stats, s);
+    if (rc == B200_OK) {
+      B200_CUDA_OK(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      p->t_max_row = h_stats[0];
+    }
+    cudaFree(d_stats);
+    if (rc != B200_OK) return rc;
     p->t_built = true;
     p->t_val_stale = false;
   } else if (p->t_val_stale) {
@@ -239,11 +253,12 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
   if (!strcmp(name, "tc_mode")) { options().tc_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "tc_nt")) {
-    B200_REQUIRE(value == 0 || (value % 32 == 0 && value >= 32 && value <= 256), "tc_nt must be 0 or a multiple of 32 up to 256");
+    B200_REQUIRE(value == 0 || (value % 64 == 0 && value >= 64 && value <= 256), "tc_nt must be 0 or a multiple of 64 up to 256");
     options().tc_nt = (int)value; return B200_OK;
   }
   if (!strcmp(name, "tc_terms")) { options().tc_terms = (int)value & 7; return B200_OK; }
-  if (!strcmp(name, "tc_split_acc")) { options().tc_split_acc = value ? 1 : 0; return B200_OK; }
+  if (!strcmp(name, "tc_chunk")) { options().tc_chunk = (int)std::max<int64_t>(1, value); return B200_OK; }
+  if (!strcmp(name, "tc_kind")) { options().tc_kind = value ? 1 : 0; return B200_OK; }
   if (!strcmp(name, "tc_min_density_pct")) { options().tc_min_density_pct = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
   return B200_ERR_INVALID;
@@ -257,7 +272,8 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "tc_mode")) return options().tc_mode;
   if (!strcmp(name, "tc_nt")) return options().tc_nt;
   if (!strcmp(name, "tc_terms")) return options().tc_terms;
-  if (!strcmp(name, "tc_split_acc")) return options().tc_split_acc;
+  if (!strcmp(name, "tc_chunk")) return options().tc_chunk;
+  if (!strcmp(name, "tc_kind")) return options().tc_kind;
   if (!strcmp(name, "tc_min_density_pct")) return options().tc_min_density_pct;
   return -1;
 }
@@ -430,6 +446,7 @@ int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
   cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd); cudaFree(p->d_peers);
+  cudaFree(p->cnt[0]); cudaFree(p->cnt[1]);
   cudaFree(p->hB); cudaFree(p->hC); cudaFree(p->tc_ws);
   tc_store_free(&p->tc[0]); tc_store_free(&p->tc[1]);
   for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
@@ -455,7 +472,8 @@ int b200_plan_stats(const b200_plan* p, int64_t* max_row_nnz, int64_t* empty_row
 
 static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M,
                      int K, int max_row, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
-                     cudaStream_t s, float* const* peer_C = nullptr, int n_peers = 0, float* mc_C = nullptr) {
+                     cudaStream_t s, float* const* peer_C = nullptr, int n_peers = 0, float* mc_C = nullptr,
+                     const float* d_bias = nullptr, int relu = 0) {
   B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
   B200_REQUIRE(ldb >= N && ldc >= N, "leading dimension smaller than N");
   B200_REQUIRE(ldb < 0x7fffffffLL && ldc < 0x7fffffffLL, "leading dimension out of range");
@@ -470,6 +488,21 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
   FwdParams q{};
   q.row_ptr = row_ptr; q.col = col; q.val = val; q.M = M; q.nnz = p->nnz;
   q.B = d_B; q.ldb = ldb; q.N = (int)N; q.C = d_C; q.ldc = ldc; q.stage = -1;
+  q.bias = d_bias; q.relu = relu;
+  if (p->bnd_valid[side] && p->pick[side].may_split) {
+    // the counters return to zero at the end of every launch, so one zeroed set serves every call; it only has
+    // to be large enough for the widest slab count seen (vector width 1: one slab per 32 columns at least 4 wide)
+    FwdPick k = p->pick[side];
+    k.slabs = (int)((N + 3) / 4 + 1);
+    const size_t need = fwd_counter_bytes(k);
+    if (p->cnt_bytes[side] < need) {
+      if (p->cnt[side]) { B200_CUDA_OK(cudaStreamSynchronize(s)); B200_CUDA_OK(cudaFree(p->cnt[side])); p->cnt[side] = nullptr; p->cnt_bytes[side] = 0; }
+      B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->cnt[side]), need));
+      B200_CUDA_OK(cudaMemsetAsync(p->cnt[side], 0, need, s));
+      p->cnt_bytes[side] = need;
+    }
+    q.counters = p->cnt[side];
+  }
   const PeerSet* d_peers = nullptr;
   if (n_peers > 0 || mc_C != nullptr) {
     PeerSet ps{};
@@ -495,6 +528,7 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
   if (mode == 0 && !(flags & B200_OP_FORCE_TC)) return false;
   if (M <= 0 || K <= 0 || p->nnz <= 0 || N <= 0) return false;
   const int64_t MB = (M + 127) / 128, KT = (K + 31) / 32;
+  if (N < 8) return false;
   if (MB * KT > ((int64_t)1 << 26)) return false;
   if (std::min<int64_t>(MB * KT, p->nnz) * 32768 > ((int64_t)24 << 30)) return false;  // densified tiles
   if ((flags & B200_OP_FORCE_TC) || mode == 2) return true;
@@ -507,8 +541,10 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
 static int plan_ensure_tc(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M,
                           int K, cudaStream_t s) {
   if (p->tc_failed[side]) return B200_ERR_ALLOC;
-  if (!p->tc_built[side]) {
-    int rc = tc_store_build(row_ptr, col, val, M, K, p->nnz, &p->tc[side], s);
+  if (!p->tc_built[side] || p->tc[side].kind != options().tc_kind) {
+    if (p->tc_built[side]) tc_store_free(&p->tc[side]);
+    p->tc_built[side] = false;
+    int rc = tc_store_build(row_ptr, col, val, M, K, p->nnz, options().tc_kind, &p->tc[side], s);
     if (rc != B200_OK) {
       p->tc_failed[side] = true;
       return rc;
@@ -542,7 +578,7 @@ static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* c
     rc = plan_ensure_tc(p, side, row_ptr, col, val, M, K, s);
     if (rc == B200_OK) {
       const int nt = options().tc_nt > 0 ? options().tc_nt : tc_pick_nt(p->tc[side].MB, (int)N, device_sm_count());
-      const size_t need = tc_pack_b_bytes(K, (int)N, nt);
+      const size_t need = tc_pack_b_bytes(K, (int)N, nt, p->tc[side].kind);
       if (p->tc_ws_bytes < need) {
         if (p->tc_ws) { B200_CUDA_OK(cudaStreamSynchronize(s)); B200_CUDA_OK(cudaFree(p->tc_ws)); p->tc_ws = nullptr; p->tc_ws_bytes = 0; }
         if (cudaMalloc(&p->tc_ws, need) != cudaSuccess) {
@@ -551,24 +587,24 @@ static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* c
           return B200_ERR_ALLOC;
         }
         p->tc_ws_bytes = need;
+        B200_CUDA_OK(cudaMemsetAsync(p->tc_ws, 0, 256, s));  // control words: the kernels keep them zero afterwards
       }
-      rc = launch_tc_forward(p->tc[side], d_B, ldb, (int)N, d_C, ldc, d_bias, flags, p->tc_ws, p->tc_ws_bytes, nt, s);
-      if (rc) return rc;
-      // stands in only when the packer saw Inf/NaN in the dense operand (device-side flag, no host sync)
-      rc = launch_spmm_strided(row_ptr, col, val, M, (int)N, d_B, bt ? 1 : ldb, bt ? ldb : 1, d_C, ct ? 1 : ldc,
-                               ct ? ldc : 1, d_bias, relu, reinterpret_cast<const int*>(p->tc_ws), s);
+      // (Inf/NaN in the dense operand are found by the packer: that launch then runs in CSR order, no host sync)
+      rc = launch_tc_forward(p->tc[side], row_ptr, col, val, d_B, ldb, (int)N, d_C, ldc, d_bias, flags, p->tc_ws,
+                             p->tc_ws_bytes, nt, s);
       p->last_path = 1;
       return rc;
     }
     if (flags & B200_OP_FORCE_TC) return rc;  // otherwise fall through to the gather kernels
   }
-  if (bt || ct || relu || d_bias != nullptr) {
+  if (bt || ct) {  // transposed operands on a matrix too sparse for the tiles: plain CSR-order kernel
     p->last_path = 2;
     return launch_spmm_strided(row_ptr, col, val, M, (int)N, d_B, bt ? 1 : ldb, bt ? ldb : 1, d_C, ct ? 1 : ldc,
-                               ct ? ldc : 1, d_bias, relu, nullptr, s);
+                               ct ? ldc : 1, d_bias, relu, s);
   }
   p->last_path = 0;
-  return plan_spmm(p, side, row_ptr, col, val, M, K, max_row, d_B, ldb, N, d_C, ldc, s);
+  return plan_spmm(p, side, row_ptr, col, val, M, K, max_row, d_B, ldb, N, d_C, ldc, s, nullptr, 0, nullptr, d_bias,
+                   relu ? 1 : 0);
 }
 
 int b200_plan_forward(b200_plan* p, const float* d_B, int64_t ldb, int64_t N, float* d_C, int64_t ldc,
@@ -593,6 +629,11 @@ int b200_plan_backward_B_ex(b200_plan* p, const float* d_G, int64_t ldg, int64_t
   if (rc) return rc;
   return plan_spmm_ex(p, 1, p->t_row_ptr, p->t_col, p->t_val, p->K, p->M, p->t_max_row, d_G, ldg, N, d_dB, lddb,
                       nullptr, flags, (cudaStream_t)stream);
+}
+
+int b200_plan_would_use_tc(const b200_plan* p, int side, int64_t N, uint32_t flags) {
+  if (p == nullptr || (side != 0 && side != 1) || p->tc_failed[side]) return 0;
+  return plan_wants_tc(p, side == 0 ? p->M : p->K, side == 0 ? p->K : p->M, N, flags) ? 1 : 0;
 }
 
 int b200_plan_tc_info(const b200_plan* p, int side, int64_t* n_tiles, int64_t* tile_bytes, int* last_path) {

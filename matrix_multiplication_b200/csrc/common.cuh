@@ -56,7 +56,8 @@ struct Options {
   int tc_mode = 1;         // 0 = never, 1 = auto (density / N rule), 2 = whenever the shape allows it
   int tc_nt = 0;           // tile width override (multiple of 32, <= 256); 0 = auto
   int tc_terms = 7;        // which split-precision products are issued: 1 hi*hi, 2 hi*lo, 4 lo*hi
-  int tc_split_acc = 0;    // 1 = correction terms accumulate in their own TMEM columns
+  int tc_chunk = 4;        // k-tiles accumulated in TMEM between two fp32 register accumulations
+  int tc_kind = 1;         // 0 = tf32 hi/lo split, 1 = fp16 hi/lo split with row / column scaling (default)
   int tc_min_density_pct = 4;  // auto rule: nnz / (M*K) at or above this percentage
 };
 Options& options();
@@ -179,6 +180,10 @@ struct Vec<4> {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  __device__ __forceinline__ void load_cg(const float* p) {  // L2 only: data written by other SMs in this launch
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   __device__ __forceinline__ void store_stream(float* p) const {
     __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
   }
@@ -194,6 +199,10 @@ struct Vec<2> {
     float2 t = __ldg(reinterpret_cast<const float2*>(p));
     v[0] = t.x; v[1] = t.y;
   }
+  __device__ __forceinline__ void load_cg(const float* p) {
+    float2 t = __ldcg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  }
   __device__ __forceinline__ void store_stream(float* p) const {
     __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
   }
@@ -206,6 +215,7 @@ template <>
 struct Vec<1> {
   float v[1];
   __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void load_cg(const float* p) { v[0] = __ldcg(p); }
   __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, v[0]); }
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
   __device__ __forceinline__ void store_mc(float* p) const { multimem_st(p, v[0]); }
@@ -225,7 +235,11 @@ struct FwdParams {
   float* C;
   long long ldc;
   float* pieces;   // workspace: [2 * n_tasks][N] partial rows of split heavy rows
+  int* counters;   // [n_tasks * column slabs] arrival counters of the pieces, zero between launches; null = the
+                   // launcher zeroes a set inside the workspace
   int stage;       // 1 / 0 force TMA staging on / off, -1 = process option
+  const float* bias;  // optional [M]: added to every column of the finished row
+  int relu;           // max(x, 0) on the finished row
 };
 // multi-GPU epilogue (row-sharded A): every finished row of C is also stored into the same row block of
 // the other ranks' buffers — plain P2P stores to mapped peer pointers, or one multimem.st to an NVLS
@@ -254,6 +268,7 @@ struct FwdPick {
 FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2, int max_row);
 size_t fwd_workspace_bytes(long long M, long long nnz, long long N);
 size_t fwd_bounds_bytes(int n_tasks);
+size_t fwd_counter_bytes(const FwdPick& k);
 int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s);
 // cached_bnd / cached_pick: boundaries a plan computed earlier for the same (W, heavy, n_tasks); may be null
 int launch_spmm_forward(const FwdParams& p, void* workspace, size_t workspace_bytes,
@@ -277,25 +292,27 @@ int launch_block_diag(const int* row_ptr, int* col, int rows, int M, int K, cuda
 // block-dense tensor-core path (tc_gemm.cu): the non-empty 128 x 32 tiles of a CSR matrix, densified
 struct TcStore {
   int M = 0, K = 0, MB = 0, KT = 0, n_tiles = 0;
+  int kind = 0;                   // element kind of the split (0 tf32, 1 fp16)
+  float* row_scale = nullptr;     // [M] fp16 kind: factor that undoes the per-row scaling of A
   int* blk_ptr = nullptr;         // [MB + 1] first stored tile of every 128-row block
   int* blk_kt = nullptr;          // [n_tiles] k-tile index of every stored tile
   int* scan = nullptr;            // [MB * KT] slot of tile (mb, kt) (exclusive scan of the occupancy flags)
   unsigned char* tiles = nullptr; // n_tiles x 32 KB (hi/lo swizzled atoms)
   size_t tile_bytes = 0;
 };
-int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz, TcStore* st,
-                   cudaStream_t s);
+int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz, int kind,
+                   TcStore* st, cudaStream_t s);
 int tc_store_refresh(const int* row_ptr, const int* col, const float* val, int nnz, TcStore* st, cudaStream_t s);
 void tc_store_free(TcStore* st);
 int tc_pick_nt(int MB, int N, int sms);
-size_t tc_pack_b_bytes(int K, int N, int nt);
-int launch_tc_forward(const TcStore& st, const float* B, long long ldb, int N, float* C, long long ldc,
-                      const float* bias, unsigned flags, void* ws, size_t ws_bytes, int nt, cudaStream_t s);
-// generic strided CSR SpMM (any B / C strides, bias, ReLU): the correctness fallback of the extended forward;
-// skipped on the device when run_if != nullptr and *run_if == 0
+size_t tc_pack_b_bytes(int K, int N, int nt, int kind);
+int launch_tc_forward(const TcStore& st, const int* row_ptr, const int* col, const float* val, const float* B,
+                      long long ldb, int N, float* C, long long ldc, const float* bias, unsigned flags, void* ws,
+                      size_t ws_bytes, int nt, cudaStream_t s);
+// generic strided CSR SpMM (any B / C strides, bias, ReLU): the correctness fallback of the extended forward
 int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, int M, int N, const float* B,
                         long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,
-                        const float* bias, bool relu, const int* run_if, cudaStream_t s);
+                        const float* bias, bool relu, cudaStream_t s);
 
 // per-device cached scratch (grown on demand; stream-ordered use only)
 int get_scratch(size_t bytes, void** ptr);

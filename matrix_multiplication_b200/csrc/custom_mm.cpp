@@ -17,6 +17,7 @@
 #include <cublas_v2.h>
 #include <torch/extension.h>
 
+#include <climits>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -126,6 +127,8 @@ void gemm_rowmajor(const float* A, const float* B, float* C, int64_t a_rows, int
   const int64_t kb = transb ? b_cols : b_rows;
   TORCH_CHECK(k == kb, "inner dimensions differ: ", k, " vs ", kb);
   if (c_rows == 0 || c_cols == 0) return;
+  TORCH_CHECK(c_rows <= INT_MAX && c_cols <= INT_MAX && k <= INT_MAX && a_cols <= INT_MAX && b_cols <= INT_MAX &&
+              batch <= INT_MAX, "cuBLAS takes 32-bit dimensions");
   auto handle = at::cuda::getCurrentCUDABlasHandle();
   const float alpha = 1.f, beta = 0.f;
   cublasStatus_t st;
@@ -225,10 +228,10 @@ void layer_mm(Layer& L, const torch::Tensor& B, torch::Tensor& C, bool row_major
     check(b200_plan_forward(L.plan, B.data_ptr<float>(), L.N, L.N, C.data_ptr<float>(), L.N, cur_stream()));
     return;
   }
-  auto Brm = B.view({L.N, L.K}).t().contiguous();  // [K, N] row-major
-  auto Crm = torch::empty({L.M, L.N}, B.options());
-  check(b200_plan_forward(L.plan, Brm.data_ptr<float>(), L.N, L.N, Crm.data_ptr<float>(), L.N, cur_stream()));
-  C.view({L.N, L.M}).copy_(Crm.t());
+  // column-major B [K,N] is B^T [N,K] row-major, column-major C is C^T [N,M] row-major: the engine reads / writes
+  // them in place (no transposed copies)
+  check(b200_plan_forward_ex(L.plan, B.data_ptr<float>(), L.K, L.N, C.data_ptr<float>(), L.M, nullptr,
+                             B200_OP_B_TRANSPOSED | B200_OP_C_TRANSPOSED, cur_stream()));
 }
 
 void cusparse_inspect(torch::Tensor displ, torch::Tensor colindex, torch::Tensor value, int nnz, int M,
@@ -358,6 +361,83 @@ torch::Tensor sddmm(torch::Tensor offsets, torch::Tensor columns, int64_t M, int
   return out;
 }
 
+// ---- plan object for matmuls.py / layers.py --------------------------------------------------------------
+// One inspected CSR operand: keeps the arrays alive, owns a b200_plan (cached merge-path boundaries, cached
+// transposed CSR, densified tiles of the block-dense tensor-core path).  This is the inspect / execute / clean triple
+// of the reference's layer registries (src/custom_mm.cpp:236-281) as an object whose lifetime follows the tensor.
+struct PlanHandle {
+  torch::Tensor offsets, columns, values;
+  int64_t M = 0, K = 0, nnz = 0;
+  b200_plan* plan = nullptr;
+
+  PlanHandle(torch::Tensor crow, torch::Tensor col, torch::Tensor val, int64_t M_, int64_t K_)
+      : offsets(std::move(crow)), columns(std::move(col)), values(std::move(val)), M(M_), K(K_) {
+    nnz = values.numel();
+    check_csr(values, columns, offsets, nnz, M);
+    c10::cuda::CUDAGuard guard(values.device());
+    check(b200_plan_create(offsets.data_ptr<int>(), columns.data_ptr<int>(), values.data_ptr<float>(), M, K, nnz,
+                           &plan, cur_stream()));
+  }
+  ~PlanHandle() { b200_plan_destroy(plan); }
+  PlanHandle(const PlanHandle&) = delete;
+  PlanHandle& operator=(const PlanHandle&) = delete;
+
+  // C = A * B (+bias, ReLU); flags: B200_OP_* (transposed operands are described by the flags, the tensors are
+  // plain row-major 2-D)
+  torch::Tensor forward(const torch::Tensor& B, torch::Tensor C, const c10::optional<torch::Tensor>& bias,
+                        int64_t flags) {
+    check_dense(B, "B");
+    check_dense(C, "C");
+    const bool bt = flags & B200_OP_B_TRANSPOSED, ct = flags & B200_OP_C_TRANSPOSED;
+    const int64_t N = bt ? B.size(0) : B.size(1);
+    TORCH_CHECK((bt ? B.size(1) : B.size(0)) == K, "dense operand does not match A's ", K, " columns");
+    TORCH_CHECK((ct ? C.size(1) : C.size(0)) == M && (ct ? C.size(0) : C.size(1)) == N, "C has the wrong shape");
+    const float* bp = nullptr;
+    if (bias.has_value() && bias->defined()) {
+      TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kFloat32 && bias->is_contiguous() &&
+                  bias->numel() == M, "bias must be a contiguous float32 CUDA vector of A_rows elements");
+      bp = bias->data_ptr<float>();
+    }
+    c10::cuda::CUDAGuard guard(B.device());
+    check(b200_plan_forward_ex(plan, B.data_ptr<float>(), ld_of(B), N, C.data_ptr<float>(), ld_of(C), bp,
+                               (uint32_t)flags, cur_stream()));
+    return C;
+  }
+  // dB = A^T * G
+  torch::Tensor backward_B(const torch::Tensor& G, torch::Tensor dB, int64_t flags) {
+    check_dense(G, "G");
+    check_dense(dB, "dB");
+    const bool bt = flags & B200_OP_B_TRANSPOSED, ct = flags & B200_OP_C_TRANSPOSED;
+    const int64_t N = bt ? G.size(0) : G.size(1);
+    TORCH_CHECK((bt ? G.size(1) : G.size(0)) == M, "G does not match A's ", M, " rows");
+    TORCH_CHECK((ct ? dB.size(1) : dB.size(0)) == K && (ct ? dB.size(0) : dB.size(1)) == N, "dB has the wrong shape");
+    c10::cuda::CUDAGuard guard(G.device());
+    check(b200_plan_backward_B_ex(plan, G.data_ptr<float>(), ld_of(G), N, dB.data_ptr<float>(), ld_of(dB),
+                                  (uint32_t)flags, cur_stream()));
+    return dB;
+  }
+  // grad of the CSR values on A's pattern
+  torch::Tensor backward_A(const torch::Tensor& G, const torch::Tensor& B) {
+    check_dense(G, "G");
+    check_dense(B, "B");
+    TORCH_CHECK(G.size(0) == M && B.size(0) == K && G.size(1) == B.size(1), "G must be [M,N] and B [K,N]");
+    c10::cuda::CUDAGuard guard(G.device());
+    auto out = torch::empty({nnz}, G.options());
+    check(b200_plan_backward_A(plan, G.data_ptr<float>(), ld_of(G), B.data_ptr<float>(), ld_of(B), G.size(1),
+                               out.data_ptr<float>(), cur_stream()));
+    return out;
+  }
+  void values_updated() { check(b200_plan_values_updated(plan)); }
+  bool would_use_tc(int64_t N, int64_t side, int64_t flags) {
+    return b200_plan_would_use_tc(plan, (int)side, N, (uint32_t)flags) != 0;
+  }
+  int64_t last_path() {
+    int path = 0;
+    check(b200_plan_tc_info(plan, 0, nullptr, nullptr, &path));
+    return path;
+  }
+};
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -396,4 +476,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_option", [](const std::string& n, int64_t v) { check(b200_set_option(n.c_str(), v)); });
   m.def("get_option", [](const std::string& n) { return b200_get_option(n.c_str()); });
   m.def("build_info", []() { return std::string(b200_build_info()); });
+  py::class_<PlanHandle>(m, "Plan", "inspected CSR operand (b200_plan): forward / backward on cached state")
+      .def(py::init<torch::Tensor, torch::Tensor, torch::Tensor, int64_t, int64_t>(), py::arg("crow"), py::arg("col"),
+           py::arg("val"), py::arg("rows"), py::arg("cols"))
+      .def("forward", &PlanHandle::forward, py::arg("B"), py::arg("C"), py::arg("bias") = py::none(),
+           py::arg("flags") = 0)
+      .def("backward_B", &PlanHandle::backward_B, py::arg("G"), py::arg("dB"), py::arg("flags") = 0)
+      .def("backward_A", &PlanHandle::backward_A, py::arg("G"), py::arg("B"))
+      .def("values_updated", &PlanHandle::values_updated)
+      .def("would_use_tc", &PlanHandle::would_use_tc, py::arg("N"), py::arg("side") = 0, py::arg("flags") = 0)
+      .def("last_path", &PlanHandle::last_path);
+  m.attr("OP_B_TRANSPOSED") = (int)B200_OP_B_TRANSPOSED;
+  m.attr("OP_C_TRANSPOSED") = (int)B200_OP_C_TRANSPOSED;
+  m.attr("OP_RELU") = (int)B200_OP_RELU;
+  m.attr("OP_NO_TC") = (int)B200_OP_NO_TC;
+  m.attr("OP_FORCE_TC") = (int)B200_OP_FORCE_TC;
 }

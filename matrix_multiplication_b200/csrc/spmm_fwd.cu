@@ -34,14 +34,10 @@ __host__ __device__ inline int smem_capacity(int W, int heavy, int warps = WARPS
 
 __host__ __device__ inline int mask_words(int cap) { return ((cap >> 3) + 4 + 3) & ~3; }  // keeps s_col 16-byte aligned
 
-// Partition block in memory: [int fix_count, 12 B pad][Boundary x (n_tasks + 1)][int fix_list x n_tasks].
-// fix_list holds the boundaries b at which a split (heavy) row ENDS in task b: the fix-up kernel sums
-// that row's pieces there.  Everything depends only on (row_ptr, W, heavy): a plan computes it once.
+// Partition block in memory: [16 B pad][Boundary x (n_tasks + 1)].  It depends only on (row_ptr, W, heavy): a
+// plan computes it once per side.
 __host__ __device__ inline const Boundary* part_bnd(const void* part) {
   return reinterpret_cast<const Boundary*>(reinterpret_cast<const unsigned char*>(part) + 16);
-}
-__host__ __device__ inline const int* part_fix_list(const void* part, int n_tasks) {
-  return reinterpret_cast<const int*>(part_bnd(part) + (n_tasks + 1));
 }
 
 __global__ void __launch_bounds__(256)
@@ -49,15 +45,7 @@ partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int hea
                  void* __restrict__ part) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tasks) return;
-  const Boundary b = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, heavy);
-  const_cast<Boundary*>(part_bnd(part))[t] = b;
-  if (t >= 1 && t < n_tasks && b.row < M && b.nz > __ldg(row_ptr + b.row)) {  // boundary inside a row
-    const Boundary nb = merge_path_boundary(row_ptr, M, nnz, (long long)(t + 1) * W, heavy);
-    if (nb.row != b.row) {  // ... which ends in task t
-      const int slot = atomicAdd(reinterpret_cast<int*>(part), 1);
-      const_cast<int*>(part_fix_list(part, n_tasks))[slot] = t;
-    }
-  }
+  const_cast<Boundary*>(part_bnd(part))[t] = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, heavy);
 }
 
 // A finished row slab of C: local store, plus the multi-GPU epilogue (peer stores / multicast store).
@@ -75,6 +63,72 @@ __device__ __forceinline__ void store_c(float* C, const PeerArg<PEERS>& ps, long
     const int n_peers = ps.s->n_peers;
     for (int q = 0; q < n_peers; ++q) o.store_stream(ps.s->peer[q] + off);
   }
+}
+
+// Fused epilogue of a finished row: + bias[row], ReLU (both optional; the FC-layer caller,
+// benchmarks/cusparse_fc_layer.py:41-46, adds the bias as a separate pass over the output).
+template <int VEC>
+__device__ __forceinline__ void row_epilogue(const FwdParams& p, int row, Vec<VEC>& o) {
+  if (p.bias != nullptr) {
+    const float b = __ldg(p.bias + row);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o.v[v] += b;
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o.v[v] = fmaxf(o.v[v], 0.f);
+  }
+}
+
+// A task has just stored one piece (partial sum) of split row `row`.  The pieces of a row are counted on a
+// per-(row, column slab) counter; the warp whose increment completes the count adds them up in task order (a
+// fixed order: the result does not depend on who does the adding) and writes the row of C, then re-arms the
+// counter for the next launch.  This folds the former second launch (a fix-up kernel over the split rows) into
+// the main kernel: no spinning, every warp only ever waits for its own loads.
+template <int VEC, bool PEERS>
+__device__ __forceinline__ void piece_done(const FwdParams& p, const PeerArg<PEERS>& ps, int row, int W, int col0,
+                                           bool reader, int lane) {
+  const long long first_item = (long long)__ldg(p.row_ptr + row) + row;
+  const long long end_item = (long long)__ldg(p.row_ptr + row + 1) + row;  // the row-end item
+  const int t_first = (int)(first_item / W);
+  int t_end = (int)(end_item / W);
+  if (end_item % W == 0) --t_end;  // a boundary on a row-end item is moved past it (merge_path_boundary)
+  const int n_pieces = t_end - t_first + 1;
+  int* cnt = p.counters + (size_t)t_end * gridDim.y + blockIdx.y;
+  __threadfence();  // this lane's piece is visible device-wide before the count moves
+  __syncwarp();
+  int old = 0;
+  if (lane == 0) old = atomicAdd(cnt, 1);
+  old = __shfl_sync(FULL, old, 0);
+  if (old != n_pieces - 1) return;
+  __threadfence();
+  if (reader) {
+    Vec<VEC> sum;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) sum.v[v] = 0.f;
+    // piece k of the row: k = 0 is the tail piece of task t_first, k >= 1 the head piece of task t_first + k
+    const float* base = p.pieces + col0;
+    int k = 0;
+    for (; k + 4 <= n_pieces; k += 4) {
+      Vec<VEC> x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        x[u].load_cg(base + (size_t)(2 * (size_t)(t_first + k + u) + (k + u == 0 ? 1 : 0)) * p.N);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sum.v[v] += x[u].v[v];
+    }
+    for (; k < n_pieces; ++k) {
+      Vec<VEC> x;
+      x.load_cg(base + (size_t)(2 * (size_t)(t_first + k) + (k == 0 ? 1 : 0)) * p.N);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
+    }
+    row_epilogue<VEC>(p, row, sum);
+    store_c<VEC, PEERS>(p.C, ps, (long long)row * p.ldc + col0, sum);
+  }
+  if (lane == 0) *cnt = 0;
 }
 
 template <int VEC, int LPR, int U, bool STAGE>
@@ -199,11 +253,12 @@ spmm_fwd_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, in
         for (int v = 0; v < VEC; ++v) acc[v] += __shfl_xor_sync(FULL, acc[v], o);
     }
   };
-  auto emit = [&](float* dst) {  // store acc (group 0 lanes) and clear it
+  auto emit = [&](float* dst, int final_row = -1) {  // store acc (group 0 lanes) and clear it
     if (writer) {
       Vec<VEC> o;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
+      if (final_row >= 0) row_epilogue<VEC>(p, final_row, o);  // a complete row of C (pieces get it when summed)
       o.store_stream(dst);
     }
 #pragma unroll
@@ -211,6 +266,7 @@ spmm_fwd_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, in
   };
 
   // rows that END inside this task: [row, i1).  Row ends are fetched 32 at a time.
+  int head_row = -1;
   int rbase = row;
   int rcache = (rbase + lane < p.M) ? __ldg(p.row_ptr + rbase + lane + 1) : 0;
   while (row < i1) {
@@ -224,18 +280,22 @@ spmm_fwd_kernel(FwdParams p, const void* __restrict__ part, int W, int heavy, in
     reduce_groups();
     if (head) {
       emit(p.pieces + (size_t)(2 * (size_t)t) * p.N + col0);
+      head_row = row;  // counted after the loop (keeps the reduction code out of the hot path's live ranges)
       head = false;
     } else {
-      emit(p.C + (long long)row * p.ldc + col0);
+      emit(p.C + (long long)row * p.ldc + col0, row);
     }
     ++row;
   }
   // partial last row: a heavy row that goes on into the next task
-  if (i1 < p.M && j1 > pos) {
+  const bool tail = i1 < p.M && j1 > pos;
+  if (tail) {
     accumulate(pos, j1);
     reduce_groups();
     emit(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
   }
+  if (head_row >= 0) piece_done<VEC, false>(p, PeerArg<false>{0}, head_row, W, col0, writer, lane);
+  if (tail) piece_done<VEC, false>(p, PeerArg<false>{0}, i1, W, col0, writer, lane);
 }
 
 // ---- flat kernel (one lane group: N >= 32 or so) ------------------------------------------------
@@ -311,6 +371,7 @@ spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, 
           Vec<VEC> z;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) z.v[v] = 0.f;
+          row_epilogue<VEC>(p, base + b, z);
           store_c<VEC, PEERS>(p.C, ps, (long long)(base + b) * p.ldc + col0, z);
         }
       }
@@ -332,6 +393,7 @@ spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, 
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
+  int head_row = -1;
   auto emit = [&](int off) {  // the non-zero at staged offset `off` is the last one of its row
     float* dst;
     if (head) {
@@ -343,12 +405,14 @@ spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, 
       Vec<VEC> o;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
+      if (!head) row_epilogue<VEC>(p, s_rowend[off], o);
       if (PEERS && !head) {
         store_c<VEC, PEERS>(p.C, ps, dst - p.C, o);
       } else {
         o.store_stream(dst);
       }
     }
+    if (head) head_row = s_rowend[off];  // last piece of a split row: counted after the loop
     head = false;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
@@ -424,61 +488,15 @@ spmm_flat_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, 
   }
   // the task ends inside a (heavy) row: its partial sum is a piece
   const int last = j1 - 1 - a0;
-  if (((s_mask[last >> 3] >> (last & 7)) & 1u) == 0u) {
-    if (active) {
-      Vec<VEC> o;
+  const bool tail = ((s_mask[last >> 3] >> (last & 7)) & 1u) == 0u;
+  if (tail && active) {
+    Vec<VEC> o;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
-      o.store_stream(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
-    }
+    for (int v = 0; v < VEC; ++v) o.v[v] = acc[v];
+    o.store_stream(p.pieces + (size_t)(2 * (size_t)t + (head ? 0 : 1)) * p.N + col0);
   }
-}
-
-// Adds up the pieces of every split row and writes the row of C.  One CTA per (fix-list entry, slab of
-// 32 * VEC columns): warp w sums pieces w, w + 8, ... (a row of the R-MAT matrix has up to ~150), the 8
-// partial sums meet in shared memory and are added in warp order — a fixed tree, so results are
-// deterministic.  Exits at once when no row was split.
-template <int VEC, bool PEERS>
-__global__ void __launch_bounds__(256)
-spmm_fixup_kernel(FwdParams p, PeerArg<PEERS> ps, const void* __restrict__ part, int W, int n_tasks) {
-  __shared__ float s_part[8][32 * VEC];
-  const int count = *reinterpret_cast<const int*>(part);
-  const Boundary* bnd = part_bnd(part);
-  const int* list = part_fix_list(part, n_tasks);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col0 = blockIdx.y * (32 * VEC) + lane * VEC;
-  const bool active = col0 < p.N;
-  for (int e = blockIdx.x; e < count; e += gridDim.x) {
-    const int b = __ldg(list + e);
-    const int i = bnd[b].row;
-    const long long t_first = ((long long)__ldg(p.row_ptr + i) + i) / W;
-    // piece k of the row: k = 0 is the tail piece of task t_first, k >= 1 the head piece of task t_first + k
-    const int n_pieces = (int)(b - t_first) + 1;
-    Vec<VEC> sum;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) sum.v[v] = 0.f;
-    if (active) {
-      for (int k = warp; k < n_pieces; k += 8) {
-        Vec<VEC> x;
-        x.load(p.pieces + (size_t)(2 * (t_first + k) + (k == 0 ? 1 : 0)) * p.N + col0);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) sum.v[v] += x.v[v];
-      }
-    }
-    if (n_pieces > 1) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) s_part[warp][lane * VEC + v] = sum.v[v];
-      __syncthreads();
-      if (warp == 0 && active) {
-#pragma unroll
-        for (int w = 1; w < 8; ++w)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) sum.v[v] += s_part[w][lane * VEC + v];
-      }
-      __syncthreads();
-    }
-    if (warp == 0 && active) store_c<VEC, PEERS>(p.C, ps, (long long)i * p.ldc + col0, sum);
-  }
+  if (head_row >= 0) piece_done<VEC, PEERS>(p, ps, head_row, W, col0, active, lane);
+  if (tail) piece_done<VEC, PEERS>(p, ps, b1.row, W, col0, active, lane);
 }
 
 __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
@@ -489,18 +507,24 @@ __global__ void zero_rows_kernel(float* C, long long ldc, int M, int N) {
   }
 }
 
-inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
-
-template <int VEC>
-int launch_fixup(const FwdParams& p, const FwdPick& k, const void* part, cudaStream_t s, const PeerSet* peers) {
-  if (k.n_tasks <= 1 || !k.may_split) return B200_OK;
-  const int slabs = (p.N + 32 * VEC - 1) / (32 * VEC);
-  dim3 fgrid((unsigned)std::min(148 * 8, k.n_tasks), (unsigned)slabs);
-  if (peers != nullptr) spmm_fixup_kernel<VEC, true><<<fgrid, 256, 0, s>>>(p, PeerArg<true>{peers}, part, k.W, k.n_tasks);
-  else spmm_fixup_kernel<VEC, false><<<fgrid, 256, 0, s>>>(p, PeerArg<false>{0}, part, k.W, k.n_tasks);
-  B200_LAUNCH_OK("spmm_fixup_kernel");
-  return B200_OK;
+// all-empty shard of a multi-GPU forward: the zero rows must also reach the other ranks' copies of C
+__global__ void zero_rows_peers_kernel(float* C, long long ldc, int M, int N, const PeerSet* ps) {
+  const long long n = (long long)M * N;
+  float* mc = ps->mc;
+  const int n_peers = ps->n_peers;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long off = (i / N) * ldc + (i % N);
+    if (mc != nullptr) {
+      multimem_st(mc + off, 0.f);
+    } else {
+      C[off] = 0.f;
+      for (int q = 0; q < n_peers; ++q) ps->peer[q][off] = 0.f;
+    }
+  }
 }
+
+inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 template <int VEC, int LPR, bool STAGE>
 int launch_one(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream_t s, const PeerSet* peers) {
@@ -515,7 +539,7 @@ int launch_one(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStream
   dim3 grid((unsigned)((k.n_tasks + WARPS - 1) / WARPS), (unsigned)k.slabs);
   kern<<<grid, WARPS * 32, smem, s>>>(p, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_fwd_kernel");
-  return launch_fixup<VEC>(p, k, bnd, s, peers);
+  return B200_OK;
 }
 
 template <int VEC, bool TMA, int NB, int NW, int MINB, bool PEERS>
@@ -532,7 +556,7 @@ int launch_flat(const FwdParams& p, const FwdPick& k, const void* bnd, cudaStrea
   if constexpr (PEERS) pa.s = peers;
   kern<<<grid, NW * 32, smem, s>>>(p, pa, bnd, k.W, k.heavy, k.n_tasks);
   B200_LAUNCH_OK("spmm_flat_kernel");
-  return launch_fixup<VEC>(p, k, bnd, s, peers);
+  return B200_OK;
 }
 
 template <int VEC, bool TMA>
@@ -611,32 +635,44 @@ FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool al
 }
 
 size_t fwd_bounds_bytes(int n_tasks) {
-  return (16 + ((size_t)n_tasks + 2) * sizeof(Boundary) + ((size_t)n_tasks + 1) * sizeof(int) + 255) & ~(size_t)255;
+  return (16 + ((size_t)n_tasks + 2) * sizeof(Boundary) + 255) & ~(size_t)255;
+}
+
+// one int per (task, column slab): arrival counters of the split rows' pieces (zero between launches)
+size_t fwd_counter_bytes(const FwdPick& k) {
+  return k.may_split ? (((size_t)k.n_tasks * (size_t)k.slabs * sizeof(int) + 255) & ~(size_t)255) : 0;
 }
 
 size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
-  // the task size depends on (M, nnz) and the items_per_task option only, not on N or alignment
+  // upper bound over the lane layouts fwd_pick may choose for this N (alignment decides the vector width,
+  // hence the number of column slabs): counters are sized for one slab per 4 columns
   const FwdPick k = fwd_pick(M, nnz, N > 0 ? N : 1, true, true, -1);
-  return fwd_bounds_bytes(k.n_tasks) + (size_t)2 * (size_t)k.n_tasks * (size_t)N * sizeof(float);
+  const size_t slabs_max = (size_t)(N + 3) / 4 + 1;
+  return fwd_bounds_bytes(k.n_tasks) + (size_t)2 * (size_t)k.n_tasks * (size_t)N * sizeof(float) +
+         (((size_t)k.n_tasks * slabs_max * sizeof(int) + 255) & ~(size_t)255) + 256;
 }
 
 int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s) {
   const int n = k.n_tasks + 1;
-  B200_CUDA_OK(cudaMemsetAsync(part, 0, 16, s));  // fix_count
   partition_kernel<<<(n + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, k.W, k.heavy, k.n_tasks, part);
   B200_LAUNCH_OK("partition_kernel");
   return B200_OK;
 }
 
-// workspace layout: [partition block (unless cached)][pieces 2 * n_tasks * N]
+// workspace layout: [partition block (unless cached)][pieces 2 * n_tasks * N][piece counters (unless the caller
+// keeps a persistent, zeroed set: FwdParams::counters)]
 int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_bytes,
                         const void* cached_part, const FwdPick* cached_pick, cudaStream_t s,
                         const PeerSet* peers) {
   FwdParams p = pin;
   if (p.M == 0 || p.N == 0) return B200_OK;
+  if (p.nnz == 0 && (p.bias != nullptr || p.relu) && peers == nullptr) {  // all rows empty: C = epilogue(0)
+    return launch_spmm_strided(p.row_ptr, p.col, p.val, p.M, p.N, p.B, p.ldb, 1, p.C, p.ldc, 1, p.bias, p.relu != 0, s);
+  }
   if (p.nnz == 0) {  // all rows empty: C = 0
     int blocks = (int)std::min<long long>(((long long)p.M * p.N + 255) / 256, 148 * 8);
-    zero_rows_kernel<<<blocks, 256, 0, s>>>(p.C, p.ldc, p.M, p.N);
+    if (peers != nullptr) zero_rows_peers_kernel<<<blocks, 256, 0, s>>>(p.C, p.ldc, p.M, p.N, peers);
+    else zero_rows_kernel<<<blocks, 256, 0, s>>>(p.C, p.ldc, p.M, p.N);
     B200_LAUNCH_OK("zero_rows_kernel");
     return B200_OK;
   }
@@ -647,8 +683,10 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
                          cached_pick->heavy == k.heavy && cached_pick->n_tasks == k.n_tasks;
   if (use_cache) k.may_split = cached_pick->may_split;
   const size_t part_bytes = use_cache ? 0 : fwd_bounds_bytes(k.n_tasks);
-  const size_t pieces_bytes = k.may_split ? (size_t)2 * (size_t)k.n_tasks * (size_t)p.N * sizeof(float) : 0;
-  const size_t need = part_bytes + pieces_bytes;
+  const size_t pieces_bytes =
+      k.may_split ? (((size_t)2 * (size_t)k.n_tasks * (size_t)p.N * sizeof(float) + 255) & ~(size_t)255) : 0;
+  const size_t counter_bytes = (p.counters == nullptr) ? fwd_counter_bytes(k) : 0;
+  const size_t need = part_bytes + pieces_bytes + counter_bytes;
   if (workspace == nullptr && need > 0) {
     void* w = nullptr;
     int rc = get_scratch(need, &w);
@@ -672,6 +710,10 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
     part = ws;
   }
   p.pieces = reinterpret_cast<float*>(ws + part_bytes);
+  if (counter_bytes > 0) {  // no persistent counters: zero a set inside the workspace for this call
+    p.counters = reinterpret_cast<int*>(ws + part_bytes + pieces_bytes);
+    B200_CUDA_OK(cudaMemsetAsync(p.counters, 0, counter_bytes, s));
+  }
   const int want_stage = (p.stage >= 0) ? p.stage : options().stage_mode;
   const bool stage = want_stage == 1 && is_aligned(p.col, 16) && is_aligned(p.val, 16);
   return stage ? dispatch<true>(p, k, part, s, peers) : dispatch<false>(p, k, part, s, peers);

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cuda_fp16.h>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -32,15 +33,23 @@ namespace b200 {
 namespace {
 
 constexpr int BM = 128;           // rows of A per tile = UMMA M
-constexpr int BK = 32;            // tf32 per 128-byte swizzle row = k extent of a stage
 constexpr int ATOM = 2048;        // bytes of one 8-row group: hi atom (1 KB) then lo atom (1 KB)
 constexpr int A_TILE = (BM / 8) * ATOM;  // 32 KB
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter, each owns half of the tile's columns
+constexpr int TC_THREADS = (2 + EPI_WARPS) * 32;
 constexpr int MAX_STAGES = 4;
+// Element kinds.  Both use 128-byte swizzled K-major rows, so a stage covers 128 / sizeof(element) values of k
+// and one tcgen05.mma consumes 32 bytes of every row (K = 8 tf32 or 16 f16).
+constexpr int KIND_TF32 = 0;      // x = hi + lo, both tf32 (exponent range of fp32: no scaling needed)
+constexpr int KIND_F16 = 1;       // x * 2^s = hi + lo, both fp16, s per row of A / per column of B (twice the MMA rate,
+                                  // half the bytes)
+__host__ __device__ constexpr int bk_of(int kind) { return kind == KIND_F16 ? 64 : 32; }
 
-// byte offset of element (r, c) inside a 1 KB K-major SWIZZLE_128B atom (r < 8 rows of 128 B, c < 32 floats)
-__host__ __device__ __forceinline__ int sw128(int r, int c) {
-  return r * 128 + ((((c >> 2) ^ r) & 7) << 4) + ((c & 3) << 2);
+// byte offset of element (r, c) inside a 1 KB K-major SWIZZLE_128B atom: r < 8 rows of 128 B, c-th element of
+// `esz` bytes in the row.  The 16-byte chunk index is XORed with the row index (what TMA / UMMA call SWIZZLE_128B).
+__host__ __device__ __forceinline__ int sw128(int r, int c, int esz) {
+  const int b = c * esz;
+  return r * 128 + ((((b >> 4) ^ r) & 7) << 4) + (b & 15);
 }
 
 __device__ __forceinline__ float tf32_rn(float x) {
@@ -48,17 +57,42 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u & 0xffffe000u);
 }
+// fp16 scaling: values are multiplied by 2^(141 - e) where e = max(biased exponent of the row / column maximum, 15),
+// so the largest magnitude lands in [2^14, 2^15) (fp16 overflows at 65504) and results are scaled back by 2^(e - 141).
+__device__ __forceinline__ int scale_exp(uint32_t max_abs_bits) { return max((int)(max_abs_bits >> 23) & 0xff, 15); }
+__device__ __forceinline__ float scale_up(int e) { return __uint_as_float((uint32_t)(268 - e) << 23); }
+__device__ __forceinline__ float scale_down(int e) { return __uint_as_float((uint32_t)(e - 14) << 23); }
+
+template <int KIND>
+struct Split;
+template <>
+struct Split<KIND_TF32> {
+  using T = float;
+  __device__ static __forceinline__ void split(float x, float, T& hi, T& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+  }
+};
+template <>
+struct Split<KIND_F16> {
+  using T = __half;
+  __device__ static __forceinline__ void split(float x, float up, T& hi, T& lo) {
+    const float xs = x * up;
+    hi = __float2half_rn(xs);
+    lo = __float2half_rn(xs - __half2float(hi));
+  }
+};
 
 // ---- plan-time packing of A --------------------------------------------------------------------------------
 __global__ void tc_mark_tiles_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int KT,
-                                     int* __restrict__ flags) {
+                                     int bk, int* __restrict__ flags) {
   // one warp per row: mark the k-tiles this row touches
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int mb = row / BM;
   const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
-  for (int p = rs + lane; p < re; p += 32) flags[(size_t)mb * KT + (__ldg(col + p) / BK)] = 1;
+  for (int p = rs + lane; p < re; p += 32) flags[(size_t)mb * KT + (__ldg(col + p) / bk)] = 1;
 }
 
 __global__ void tc_list_tiles_kernel(const int* __restrict__ flags, const int* __restrict__ scan, int MB, int KT,
@@ -72,104 +106,242 @@ __global__ void tc_list_tiles_kernel(const int* __restrict__ flags, const int* _
   if (i == n - 1) blk_ptr[MB] = scan[i] + flags[i];
 }
 
+template <int KIND>
 __global__ void tc_pack_a_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col,
                                  const float* __restrict__ val, int M, int KT, const int* __restrict__ scan,
-                                 unsigned char* __restrict__ tiles) {
+                                 unsigned char* __restrict__ tiles, float* __restrict__ row_scale) {
+  using T = typename Split<KIND>::T;
+  constexpr int BK = bk_of(KIND);
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int mb = row / BM, r = row % BM;
   const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
+  float up = 1.f;
+  if constexpr (KIND == KIND_F16) {
+    uint32_t mx = 0;
+    for (int p = rs + lane; p < re; p += 32) {
+      const uint32_t b = __float_as_uint(__ldg(val + p)) & 0x7fffffffu;
+      mx = max(mx, b < 0x7f800000u ? b : 0u);  // Inf/NaN in A stay Inf/NaN after the split whatever the scale
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int e = scale_exp(mx);
+    up = scale_up(e);
+    if (lane == 0) row_scale[row] = scale_down(e);
+  }
   for (int p = rs + lane; p < re; p += 32) {
     const int c = __ldg(col + p);
-    const float x = __ldg(val + p);
     const int slot = scan[(size_t)mb * KT + c / BK];
     unsigned char* atom = tiles + (size_t)slot * A_TILE + (size_t)(r >> 3) * ATOM;
-    const int off = sw128(r & 7, c % BK);
-    const float hi = tf32_rn(x);
-    *reinterpret_cast<float*>(atom + off) = hi;
-    *reinterpret_cast<float*>(atom + 1024 + off) = tf32_rn(x - hi);
+    const int off = sw128(r & 7, c % BK, (int)sizeof(T));
+    T hi, lo;
+    Split<KIND>::split(__ldg(val + p), up, hi, lo);
+    *reinterpret_cast<T*>(atom + off) = hi;
+    *reinterpret_cast<T*>(atom + 1024 + off) = lo;
   }
 }
 
 // ---- per-call packing of the dense operand ----------------------------------------------------------------
-// Packed layout: [kt][n group of 8][hi atom | lo atom]; atom row = one n, its 32 k values (128 B, swizzled).
-// TRANS = false: B is [K, N] row-major (the reference's layout, src/custom_mm.cpp:203-217): a warp reads, for
-//   each of the 32 k rows of the tile, the 32-byte sector holding 8 consecutive n (lane = k) and writes full
-//   128-byte atom rows (the 32 lanes of a store cover one row).
-// TRANS = true: the operand is given as B^T [N, K] row-major (activations [tokens, features] of an FC layer):
-//   atom rows are contiguous in memory, float4 in, float4 out.
-// Rows k >= K and columns n >= N are written as zeros.  Non-finite inputs raise *nonfinite (the dense
-// contraction would turn 0 * Inf into NaN where the sparse product skips the term): the caller falls back.
+// fp16 kind, pass 1: per-column maximum magnitude (as uint bits: monotonic for non-negative floats) and the
+// non-finite flag.  TRANS = false: B [K, N] row-major, thread = column, blockIdx.y strides over k.
 template <bool TRANS>
 __global__ void __launch_bounds__(256)
+tc_colmax_kernel(const float* __restrict__ B, long long ld, int K, int N, uint32_t* __restrict__ colmax,
+                 int* __restrict__ nonfinite) {
+  if constexpr (!TRANS) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint32_t mx = 0;
+    for (int k = blockIdx.y; k < K; k += gridDim.y) mx = max(mx, __float_as_uint(__ldg(B + (long long)k * ld + n)) & 0x7fffffffu);
+    if (mx >= 0x7f800000u) { atomicOr(nonfinite, 1); mx = 0; }
+    atomicMax(colmax + n, mx);
+  } else {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n >= N) return;
+    uint32_t mx = 0;
+    for (int k = lane; k < K; k += 32) mx = max(mx, __float_as_uint(__ldg(B + (long long)n * ld + k)) & 0x7fffffffu);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+      if (mx >= 0x7f800000u) { atomicOr(nonfinite, 1); mx = 0; }
+      colmax[n] = mx;
+    }
+  }
+}
+
+// Packed layout: [kt][n group of 8][hi atom | lo atom]; atom row = one n, its BK k values (128 B, swizzled).
+// TRANS = false: B is [K, N] row-major (the reference's layout, src/custom_mm.cpp:203-217): a warp reads, for
+//   each k row of the tile, the 32-byte sector holding 8 consecutive n and writes full 128-byte atom rows
+//   (the 32 lanes of a store cover one row).
+// TRANS = true: the operand is given as B^T [N, K] row-major (activations [tokens, features] of an FC layer):
+//   atom rows are contiguous in memory, 16/32-byte vectors in and out.
+// Rows k >= K and columns n >= N are written as zeros.  Non-finite inputs raise *nonfinite (the dense
+// contraction would turn 0 * Inf into NaN where the sparse product skips the term): the caller falls back.
+// cm8: the maximum magnitudes (uint bits) of the group's 8 columns (fp16 kind), global or shared memory.
+template <int KIND, bool TRANS>
+__device__ __forceinline__ bool tc_pack_atom(const float* __restrict__ B, long long ld, int K, int N, int kt, int g,
+                                             unsigned char* __restrict__ atom, const uint32_t* cm8, int lane) {
+  using T = typename Split<KIND>::T;
+  constexpr int BK = bk_of(KIND);
+  constexpr int KL = BK / 32;  // k values per lane (non-transposed read)
+  bool bad = false;
+  const int n0 = g * 8, k0 = kt * BK;
+  if constexpr (!TRANS) {
+    // lane owns k = k0 + KL*lane .. +KL-1 (adjacent k: one 4-byte store per atom row for fp16)
+    float x[KL][8];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+      const int k = k0 + KL * lane + i;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+      if (k < K) {
+        const float* src = B + (long long)k * ld + n0;
+        if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w;
+          x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + j < N) x[i][j] = __ldg(src + j);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float up = 1.f;
+      if constexpr (KIND == KIND_F16) up = scale_up(scale_exp(cm8[j]));
+      T hi[KL], lo[KL];
+#pragma unroll
+      for (int i = 0; i < KL; ++i) {
+        bad |= !(fabsf(x[i][j]) <= 3.0e38f);
+        Split<KIND>::split(x[i][j], up, hi[i], lo[i]);
+      }
+      const int off = sw128(j, KL * lane, (int)sizeof(T));
+      if constexpr (KIND == KIND_F16) {
+        *reinterpret_cast<__half2*>(atom + off) = __halves2half2(hi[0], hi[1]);
+        *reinterpret_cast<__half2*>(atom + 1024 + off) = __halves2half2(lo[0], lo[1]);
+      } else {
+        *reinterpret_cast<T*>(atom + off) = hi[0];
+        *reinterpret_cast<T*>(atom + 1024 + off) = lo[0];
+      }
+    }
+  } else {
+    // lane -> (row rr = lane / 4, output 16-byte chunks q = lane % 4 and q + 4); a chunk holds EC = 16 / sizeof(T)
+    // consecutive k of row n
+    constexpr int EC = 16 / (int)sizeof(T);
+    const int rr = lane >> 2, n = n0 + rr;
+    float up = 1.f;
+    if constexpr (KIND == KIND_F16) up = scale_up(scale_exp(cm8[rr]));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = (lane & 3) + 4 * h;
+      const int k = k0 + EC * q;
+      float x[EC];
+#pragma unroll
+      for (int j = 0; j < EC; ++j) x[j] = 0.f;
+      if (n < N) {
+        const float* src = B + (long long)n * ld + k;
+        if (k + EC <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+          for (int v = 0; v < EC / 4; ++v) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src) + v);
+            x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < EC; ++j)
+            if (k + j < K) x[j] = __ldg(src + j);
+        }
+      }
+      T hi[EC], lo[EC];
+#pragma unroll
+      for (int j = 0; j < EC; ++j) {
+        bad |= !(fabsf(x[j]) <= 3.0e38f);
+        Split<KIND>::split(x[j], up, hi[j], lo[j]);
+      }
+      const int off = rr * 128 + (((q ^ rr) & 7) << 4);
+      *reinterpret_cast<uint4*>(atom + off) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(atom + 1024 + off) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+  return bad;
+}
+
+// one warp per atom pair, grid-stride; column maxima (fp16 kind) come from tc_colmax_kernel
+template <int KIND, bool TRANS>
+__global__ void __launch_bounds__(256)
 tc_pack_b_kernel(const float* __restrict__ B, long long ld, int K, int N, int KT, int NG,
-                 unsigned char* __restrict__ out, int* __restrict__ nonfinite) {
+                 unsigned char* __restrict__ out, const uint32_t* __restrict__ colmax, int* __restrict__ nonfinite) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int total = KT * NG;
   bool bad = false;
   for (int w = warp; w < total; w += (gridDim.x * blockDim.x) >> 5) {
     const int kt = w / NG, g = w % NG;
-    unsigned char* atom = out + ((size_t)kt * NG + g) * ATOM;
-    const int n0 = g * 8, k0 = kt * BK;
-    if constexpr (!TRANS) {
-      const int k = k0 + lane;
-      float x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = 0.f;
-      if (k < K) {
-        const float* src = B + (long long)k * ld + n0;
-        if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-          x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (n0 + j < N) x[j] = __ldg(src + j);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        bad |= !(fabsf(x[j]) <= 3.0e38f);
-        const float hi = tf32_rn(x[j]);
-        const int off = sw128(j, lane);
-        *reinterpret_cast<float*>(atom + off) = hi;
-        *reinterpret_cast<float*>(atom + 1024 + off) = tf32_rn(x[j] - hi);
-      }
-    } else {
-      // lane -> (row rr = lane / 4, 16-byte chunks q = lane % 4 and q + 4)
-      const int rr = lane >> 2, n = n0 + rr;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int q = (lane & 3) + 4 * h;
-        const int k = k0 + 4 * q;
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
-        if (n < N) {
-          const float* src = B + (long long)n * ld + k;
-          if (k + 4 <= K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (k + j < K) x[j] = __ldg(src + j);
-          }
-        }
-        float hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bad |= !(fabsf(x[j]) <= 3.0e38f);
-          hi[j] = tf32_rn(x[j]);
-          lo[j] = tf32_rn(x[j] - hi[j]);
-        }
-        const int off = rr * 128 + (((q ^ rr) & 7) << 4);
-        *reinterpret_cast<float4*>(atom + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(atom + 1024 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
-    }
+    bad |= tc_pack_atom<KIND, TRANS>(B, ld, K, N, kt, g, out + ((size_t)kt * NG + g) * ATOM, colmax + g * 8, lane);
   }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(nonfinite, 1);
+}
+
+// fp16 kind, wide operands (at least one CTA per SM): ONE kernel per call.  A CTA owns one group of 8 columns: it
+// first scans the group for the column maxima (kept in shared memory and written out for the epilogue), then packs
+// the group's atoms from the now cache-resident data.
+template <bool TRANS>
+__global__ void __launch_bounds__(256)
+tc_prepack_b_kernel(const float* __restrict__ B, long long ld, int K, int N, int KT, int NG,
+                    unsigned char* __restrict__ out, uint32_t* __restrict__ colmax, int* __restrict__ nonfinite) {
+  __shared__ uint32_t s_max[8];
+  const int g = blockIdx.x, n0 = g * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 8) s_max[threadIdx.x] = 0u;
+  __syncthreads();
+  bool bad = false;
+  if constexpr (!TRANS) {
+    uint32_t mx[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const bool vec = n0 + 8 <= N && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(B + n0) & 15) == 0);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float* src = B + (long long)k * ld + n0;
+      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < N) x[j] = __ldg(src + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx[j] = max(mx[j], __float_as_uint(x[j]) & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) mx[j] = max(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+      if (lane == 0) atomicMax(&s_max[j], mx[j]);
+    }
+  } else {
+    const int n = n0 + warp;  // 8 warps, 8 rows of B^T
+    uint32_t mx = 0u;
+    if (n < N)
+      for (int k = lane; k < K; k += 32) mx = max(mx, __float_as_uint(__ldg(B + (long long)n * ld + k)) & 0x7fffffffu);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_max[warp] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    uint32_t m = s_max[threadIdx.x];
+    if (m >= 0x7f800000u) { bad = true; m = 0u; }
+    s_max[threadIdx.x] = m;
+    colmax[n0 + threadIdx.x] = m;
+  }
+  __syncthreads();
+  for (int kt = warp; kt < KT; kt += 8)
+    bad |= tc_pack_atom<KIND_F16, TRANS>(B, ld, K, N, kt, g, out + ((size_t)kt * NG + g) * ATOM, s_max, lane);
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(nonfinite, 1);
 }
 
@@ -215,15 +387,25 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, one elected thread issues.  SASS: UTCHMMA (tf32 flavour).
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, one elected thread issues.  SASS: UTCHMMA.
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (KIND == KIND_F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -231,8 +413,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 // 32 lanes x 32 consecutive columns of 32-bit TMEM -> 32 registers per thread (thread = lane = row).  SASS: LDTM
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
@@ -243,10 +424,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups `sbo` bytes apart (sm_100 version bit)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo) {
@@ -257,9 +436,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo) 
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
-// instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, M = 128, N = nt
-__host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(int nt) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32 (format 2) or f16 (format 0), both K-major, M = 128, N = nt
+__host__ __device__ __forceinline__ uint32_t umma_idesc(int kind, int nt) {
+  const uint32_t fmt = kind == KIND_F16 ? 0u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct TcParams {
@@ -272,18 +452,71 @@ struct TcParams {
   long long ldc;
   int M, N;
   const float* bias;
+  const float* row_scale;      // fp16 kind: 2^(e - 141) per row of A / from the column maxima of B; else null
+  const uint32_t* colmax;
   unsigned flags;
   int MB, NB, Nt;
   int stages;
-  int split_acc;   // 1: correction terms accumulate in their own TMEM columns, added in the epilogue
+  int chunk;       // k-tiles accumulated in TMEM before the epilogue warps fold them into their fp32 registers
   int terms;       // bit 0 hi*hi, bit 1 hi*lo, bit 2 lo*hi (debug / accuracy studies; 7 = all)
-  const int* skip_if;  // the packer's non-finite flag: when set the kernel leaves C to the gather path
-  int* dbg;        // [0] = first wait that timed out (0 = none)
+  int* ctl;        // [0] the packer's non-finite flag: when set this launch computes C in CSR order instead (0 * Inf
+                   //     must stay out of the result); [1] first pipeline wait that timed out (debug); [2] exit ticket
+  // the CSR and the raw dense operand, for that CSR-order pass
+  const int* row_ptr;
+  const int* col;
+  const float* val;
+  const float* B;
+  long long b_sk, b_sn;
 };
 
+// exit protocol: the last CTA to leave re-arms the non-finite flag and the ticket for the next launch
+__device__ __forceinline__ void tc_exit_ticket(int* ctl) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ctl + 2, 1) == (int)gridDim.x - 1) {
+      ctl[0] = 0;
+      ctl[2] = 0;
+    }
+  }
+}
+
+// C = A * B in CSR order with any strides (+bias, ReLU): warp per (row, 32-column slab)
+__device__ __forceinline__ void csr_order_spmm(const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                               const float* __restrict__ val, int M, int N, const float* __restrict__ B,
+                                               long long b_sk, long long b_sn, float* __restrict__ C, long long c_sm,
+                                               long long c_sn, const float* __restrict__ bias, bool relu) {
+  const int lane = threadIdx.x & 31;
+  const int slabs = (N + 31) / 32;
+  const long long total = (long long)M * slabs;
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
+       w += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int row = (int)(w / slabs), n = (int)(w % slabs) * 32 + lane;
+    const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
+    if (n < N) {
+      float acc = 0.f;
+      for (int p = rs; p < re; ++p)
+        acc = fmaf(__ldg(val + p), __ldg(B + (long long)__ldg(col + p) * b_sk + (long long)n * b_sn), acc);
+      if (bias != nullptr) acc += __ldg(bias + row);
+      if (relu) acc = fmaxf(acc, 0.f);
+      C[(long long)row * c_sm + (long long)n * c_sn] = acc;
+    }
+  }
+}
+
+// The tensor core adds into its TMEM accumulator with truncation (measured: a K = 16384 contraction of positive
+// values comes out 1.3e-4 low), so an accumulator only ever holds `chunk` k-tiles (<= 48 additions, bias <= 1.5e-6
+// of the partial sum); the epilogue warps add the partial sums in fp32 registers with round-to-nearest.  The two
+// TMEM buffers alternate per chunk: MMAs of chunk i+1 overlap the drain of chunk i.
+template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p) {
   extern __shared__ unsigned char tc_smem_raw[];
-  if (p.skip_if != nullptr && *reinterpret_cast<const volatile int*>(p.skip_if) != 0) return;
+  if (*reinterpret_cast<const volatile int*>(p.ctl) != 0) {  // Inf / NaN in the dense operand (uniform over the grid)
+    const bool ctr = (p.flags & 2u) != 0;
+    csr_order_spmm(p.row_ptr, p.col, p.val, p.M, p.N, p.B, p.b_sk, p.b_sn, p.C, ctr ? 1 : p.ldc, ctr ? p.ldc : 1, p.bias,
+                   (p.flags & 4u) != 0);
+    tc_exit_ticket(p.ctl);
+    return;
+  }
 
   const uint32_t raw = smem_u32(tc_smem_raw);
   unsigned char* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);  // swizzle atoms need 1 KB alignment
@@ -295,8 +528,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int acc_cols = p.Nt * (p.split_acc ? 2 : 1);
-  const int acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -305,7 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, 4);  // one arrive per epilogue warp
+      mbar_init(acc_empty + i, EPI_WARPS);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -326,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
         const int mb = tile / p.NB, nb = tile % p.NB;
         const int t0 = __ldg(p.blk_ptr + mb), t1 = __ldg(p.blk_ptr + mb + 1);
         for (int t = t0; t < t1; ++t) {
-          ok = mbar_wait_bounded(empty + stage, phase ^ 1u, p.dbg, 100 + stage);
+          ok = mbar_wait_bounded(empty + stage, phase ^ 1u, p.ctl + 1, 100 + stage);
           if (!ok) break;
           const int kt = __ldg(p.blk_kt + t);
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
@@ -341,104 +572,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
   } else if (warp == 1) {
     // ===== MMA issuer: one lane issues every tcgen05.mma of this CTA =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(p.Nt);
+      const uint32_t idesc = umma_idesc(KIND, p.Nt);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
+      uint32_t g = 0;  // chunks issued so far: TMEM buffer g & 1, its barrier phase (g >> 1) & 1
       bool ok = true;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int mb = tile / p.NB;
-        const int as = it % acc_stages;
-        const uint32_t aphase = (uint32_t)(it / acc_stages) & 1u;
-        ok = mbar_wait_bounded(acc_empty + as, aphase ^ 1u, p.dbg, 200 + as);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(as * acc_cols);
-        const uint32_t d_corr = p.split_acc ? d_main + (uint32_t)p.Nt : d_main;
         const int t0 = __ldg(p.blk_ptr + mb), t1 = __ldg(p.blk_ptr + mb + 1);
-        uint32_t acc_main = 0, acc_corr = 0;
-        for (int t = t0; t < t1; ++t) {
-          ok = mbar_wait_bounded(full + stage, phase, p.dbg, 300 + stage);
+        for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
+          const int as = (int)(g & 1u);
+          ok = mbar_wait_bounded(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + A_TILE;
+          const uint32_t d = tmem_base + (uint32_t)(as * p.Nt);
+          uint32_t acc = 0;
+          const int c1 = min(c0 + p.chunk, t1);
+          for (int t = c0; t < c1; ++t) {
+            ok = mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + A_TILE;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
-            const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
-            const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
-            uint32_t& acc_c = p.split_acc ? acc_corr : acc_main;  // the enable-input-D bit of the target columns
-            if (p.terms & 2) { umma_tf32(d_corr, a_hi, b_lo, idesc, acc_c); acc_c = 1; }
-            if (p.terms & 4) { umma_tf32(d_corr, a_lo, b_hi, idesc, acc_c); acc_c = 1; }
-            if (p.terms & 1) { umma_tf32(d_main, a_hi, b_hi, idesc, acc_main); acc_main = 1; }
+            for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of every swizzled 128-byte row
+              const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
+              const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
+              if (p.terms & 2) { umma<KIND>(d, a_hi, b_lo, idesc, acc); acc = 1; }
+              if (p.terms & 4) { umma<KIND>(d, a_lo, b_hi, idesc, acc); acc = 1; }
+              if (p.terms & 1) { umma<KIND>(d, a_hi, b_hi, idesc, acc); acc = 1; }
+            }
+            umma_commit(empty + stage);  // the smem slot is free once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(empty + stage);  // the smem slot is free once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          umma_commit(acc_full + as);  // partial sums of this chunk complete -> epilogue warps
         }
-        umma_commit(acc_full + as);  // accumulator complete -> epilogue
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM -> registers -> (+bias, ReLU) -> C =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ===== epilogue warps 2..9: TMEM -> fp32 registers (+=) per chunk; at tile end (+bias, ReLU) -> C =====
+    const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+    const int half = (warp - 2) >> 2;     // which half of the tile's columns
+    const int ntw = p.Nt >> 1;            // columns per warp (multiple of 32, <= 128)
     const bool relu = (p.flags & 4u) != 0, ct = (p.flags & 2u) != 0;
     const bool vec4 = !ct && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    int it = 0;
+    uint32_t g = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       const int mb = tile / p.NB, nb = tile % p.NB;
-      const int as = it % acc_stages;
-      const uint32_t aphase = (uint32_t)(it / acc_stages) & 1u;
-      const bool empty_block = __ldg(p.blk_ptr + mb) == __ldg(p.blk_ptr + mb + 1);
-      ok = mbar_wait_bounded(acc_full + as, aphase, p.dbg, 400 + as);
+      const int t0 = __ldg(p.blk_ptr + mb), t1 = __ldg(p.blk_ptr + mb + 1);
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
+        const int as = (int)(g & 1u);
+        ok = mbar_wait_bounded(acc_full + as, (g >> 1) & 1u, p.ctl + 1, 400 + as);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.Nt + half * ntw);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < ntw) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + as);  // this warp's part of the buffer is drained
+      }
       if (!ok) break;
-      tc_fence_after();
       const int m = mb * BM + q * 32 + lane;
       const float bias = (p.bias != nullptr && m < p.M) ? __ldg(p.bias + m) : 0.f;
-      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-      for (int c0 = 0; c0 < p.Nt; c0 += 32) {
-        const int n0 = nb * p.Nt + c0;
-        if (n0 >= p.N) break;
-        float v[32];
-        if (empty_block) {
+      float rs = 1.f;
+      if constexpr (KIND == KIND_F16) rs = (m < p.M) ? __ldg(p.row_scale + m) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        } else {
-          tmem_ld32(t_main + (uint32_t)c0, v);
-          if (p.split_acc) {
-            float w[32];
-            tmem_ld32(t_main + (uint32_t)(p.Nt + c0), w);
+      for (int c = 0; c < 4; ++c) {
+        const int n0 = nb * p.Nt + half * ntw + c * 32;
+        if (c * 32 < ntw && n0 < p.N) {
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          for (int j = 0; j < 32; ++j) {
+            float x = acc[c * 32 + j];
+            if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp((n0 + j < p.N) ? __ldg(p.colmax + n0 + j) : 0u));
+            x += bias;
+            v[j] = relu ? fmaxf(x, 0.f) : x;
           }
-        }
+          if (ct) {  // C^T [N, M]: a register is one n, the 32 lanes are 32 consecutive m -> coalesced
+            if (m < p.M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] += bias;
-          if (relu) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (ct) {  // C^T [N, M]: a register is one n, the 32 lanes are 32 consecutive m -> coalesced
-          if (m < p.M) {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) p.C[(long long)(n0 + j) * p.ldc + m] = v[j];
+            }
+          } else if (m < p.M) {
+            float* dst = p.C + (long long)m * p.ldc + n0;
+            if (vec4 && n0 + 32 <= p.N) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) p.C[(long long)(n0 + j) * p.ldc + m] = v[j];
-          }
-        } else if (m < p.M) {
-          float* dst = p.C + (long long)m * p.ldc + n0;
-          if (vec4 && n0 + 32 <= p.N) {
+              for (int j = 0; j < 32; j += 4)
+                __stcs(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              __stcs(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) dst[j] = v[j];
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) dst[j] = v[j];
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + as);  // this warp's quarter of the accumulator is drained
     }
   }
   tc_fence_before();
@@ -447,6 +689,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  tc_exit_ticket(p.ctl);
 }
 
 // Generic strided CSR SpMM: warp per row, lanes over 32 dense columns, any element strides for B and C, bias
@@ -455,37 +698,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
 __global__ void __launch_bounds__(256)
 spmm_strided_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
                     int M, int N, const float* __restrict__ B, long long b_sk, long long b_sn, float* __restrict__ C,
-                    long long c_sm, long long c_sn, const float* __restrict__ bias, int relu,
-                    const int* __restrict__ run_if) {
-  if (run_if != nullptr && *reinterpret_cast<const volatile int*>(run_if) == 0) return;
-  const int lane = threadIdx.x & 31;
-  const int slabs = (N + 31) / 32;
-  const long long total = (long long)M * slabs;
-  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
-       w += ((long long)gridDim.x * blockDim.x) >> 5) {
-    const int row = (int)(w / slabs), n = (int)(w % slabs) * 32 + lane;
-    const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
-    float acc = 0.f;
-    if (n < N) {
-      for (int p = rs; p < re; ++p)
-        acc = fmaf(__ldg(val + p), __ldg(B + (long long)__ldg(col + p) * b_sk + (long long)n * b_sn), acc);
-      if (bias != nullptr) acc += __ldg(bias + row);
-      if (relu) acc = fmaxf(acc, 0.f);
-      C[(long long)row * c_sm + (long long)n * c_sn] = acc;
-    }
-  }
+                    long long c_sm, long long c_sn, const float* __restrict__ bias, int relu) {
+  csr_order_spmm(row_ptr, col, val, M, N, B, b_sk, b_sn, C, c_sm, c_sn, bias, relu != 0);
 }
 
 }  // namespace
 
 int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, int M, int N, const float* B,
                         long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,
-                        const float* bias, bool relu, const int* run_if, cudaStream_t s) {
+                        const float* bias, bool relu, cudaStream_t s) {
   if (M == 0 || N == 0) return B200_OK;
   const long long warps = (long long)M * ((N + 31) / 32);
   const int blocks = (int)std::min<long long>((warps + 7) / 8, (long long)device_sm_count() * 16);
   spmm_strided_kernel<<<blocks, 256, 0, s>>>(row_ptr, col, val, M, N, B, b_sk, b_sn, C, c_sm, c_sn, bias,
-                                              relu ? 1 : 0, run_if);
+                                              relu ? 1 : 0);
   B200_LAUNCH_OK("spmm_strided_kernel");
   return B200_OK;
 }
@@ -493,18 +719,30 @@ int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, in
 // ---- host side ------------------------------------------------------------------------------------------------
 
 void tc_store_free(TcStore* st) {
-  cudaFree(st->blk_ptr); cudaFree(st->blk_kt); cudaFree(st->scan); cudaFree(st->tiles);
+  cudaFree(st->blk_ptr); cudaFree(st->blk_kt); cudaFree(st->scan); cudaFree(st->tiles); cudaFree(st->row_scale);
   *st = TcStore{};
 }
 
-// Densify the non-empty 128 x 32 tiles of a CSR matrix into hi/lo swizzled tiles.  Synchronises the stream once
+static int tc_launch_pack_a(const int* row_ptr, const int* col, const float* val, int nnz, TcStore* st, cudaStream_t s) {
+  if (nnz == 0) return B200_OK;
+  const unsigned wblocks = (unsigned)(((size_t)st->M * 32 + 255) / 256);
+  if (st->kind == KIND_F16)
+    tc_pack_a_kernel<KIND_F16><<<wblocks, 256, 0, s>>>(row_ptr, col, val, st->M, st->KT, st->scan, st->tiles, st->row_scale);
+  else
+    tc_pack_a_kernel<KIND_TF32><<<wblocks, 256, 0, s>>>(row_ptr, col, val, st->M, st->KT, st->scan, st->tiles, st->row_scale);
+  B200_LAUNCH_OK("tc_pack_a_kernel");
+  return B200_OK;
+}
+
+// Densify the non-empty 128 x BK tiles of a CSR matrix into hi/lo swizzled tiles.  Synchronises the stream once
 // (the number of non-empty tiles sizes the allocation).
-int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz, TcStore* st,
+int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz, int kind, TcStore* st,
                    cudaStream_t s) {
   *st = TcStore{};
-  st->M = M; st->K = K;
+  st->M = M; st->K = K; st->kind = kind;
+  const int bk = bk_of(kind);
   st->MB = (M + BM - 1) / BM;
-  st->KT = (K + BK - 1) / BK;
+  st->KT = (K + bk - 1) / bk;
   const size_t cells = (size_t)st->MB * st->KT;
   if (cells == 0 || cells > ((size_t)1 << 26)) {
     set_error("block-dense store: %zu candidate tiles is outside the supported range", cells);
@@ -514,10 +752,11 @@ int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, 
   B200_CUDA_OK(cudaMalloc(&flags, cells * sizeof(int)));
   B200_CUDA_OK(cudaMalloc(&st->scan, cells * sizeof(int)));
   B200_CUDA_OK(cudaMalloc(&st->blk_ptr, ((size_t)st->MB + 1) * sizeof(int)));
+  B200_CUDA_OK(cudaMalloc(&st->row_scale, (size_t)std::max(M, 1) * sizeof(float)));
   B200_CUDA_OK(cudaMemsetAsync(flags, 0, cells * sizeof(int), s));
   const unsigned wblocks = (unsigned)(((size_t)M * 32 + 255) / 256);
   if (nnz > 0) {
-    tc_mark_tiles_kernel<<<wblocks, 256, 0, s>>>(row_ptr, col, M, st->KT, flags);
+    tc_mark_tiles_kernel<<<wblocks, 256, 0, s>>>(row_ptr, col, M, st->KT, bk, flags);
     B200_LAUNCH_OK("tc_mark_tiles_kernel");
   }
   size_t tmp_bytes = 0;
@@ -544,10 +783,8 @@ int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, 
   }
   st->tile_bytes = bytes;
   B200_CUDA_OK(cudaMemsetAsync(st->tiles, 0, bytes, s));
-  if (nnz > 0) {
-    tc_pack_a_kernel<<<wblocks, 256, 0, s>>>(row_ptr, col, val, M, st->KT, st->scan, st->tiles);
-    B200_LAUNCH_OK("tc_pack_a_kernel");
-  }
+  int rc = tc_launch_pack_a(row_ptr, col, val, nnz, st, s);
+  if (rc) return rc;
   B200_CUDA_OK(cudaStreamSynchronize(s));
   cudaFree(flags);
   cudaFree(tmp);
@@ -556,20 +793,16 @@ int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, 
 
 // values changed in place, pattern unchanged: rewrite the stored values (zeros stay zeros)
 int tc_store_refresh(const int* row_ptr, const int* col, const float* val, int nnz, TcStore* st, cudaStream_t s) {
-  if (nnz == 0) return B200_OK;
-  const unsigned wblocks = (unsigned)(((size_t)st->M * 32 + 255) / 256);
-  tc_pack_a_kernel<<<wblocks, 256, 0, s>>>(row_ptr, col, val, st->M, st->KT, st->scan, st->tiles);
-  B200_LAUNCH_OK("tc_pack_a_kernel");
-  return B200_OK;
+  return tc_launch_pack_a(row_ptr, col, val, nnz, st, s);
 }
 
-// Tile width: the Nt (multiple of 32, <= 256) that minimises waves x per-tile cost on `sms` persistent CTAs.
+// Tile width: the Nt (multiple of 64, <= 256) that minimises waves x per-tile cost on `sms` persistent CTAs.
 // Narrow tiles re-read A more often and are shared-memory-bound (A 4 KB + B Nt*32 B per MMA), so their
 // per-column cost is higher: cost(Nt) ~ Nt + 64.
 int tc_pick_nt(int MB, int N, int sms) {
-  int best = 32;
+  int best = 64;
   double best_cost = 1e300;
-  for (int nt = 32; nt <= 256; nt += 32) {
+  for (int nt = 64; nt <= 256; nt += 64) {
     const long long tiles = (long long)MB * ((N + nt - 1) / nt);
     const long long waves = (tiles + sms - 1) / sms;
     const double cost = (double)waves * (nt + 64);
@@ -581,44 +814,58 @@ int tc_pick_nt(int MB, int N, int sms) {
   return best;
 }
 
-size_t tc_pack_b_bytes(int K, int N, int nt) {
-  const size_t KT = (size_t)(K + BK - 1) / BK;
+// workspace: [control words, 256 B: zero between launches][column maxima, one per padded column][packed B]
+static size_t tc_colmax_bytes(int n_pad) { return (((size_t)n_pad * 4 + 255) / 256) * 256; }
+size_t tc_pack_b_bytes(int K, int N, int nt, int kind) {
+  const int bk = bk_of(kind);
+  const size_t KT = (size_t)(K + bk - 1) / bk;
   const size_t NG = (size_t)((N + nt - 1) / nt) * (nt / 8);
-  return KT * NG * ATOM + 256;  // + the non-finite flag and the debug word
+  return 256 + tc_colmax_bytes((int)NG * 8) + KT * NG * ATOM;
 }
 
-// C = A_tiles * B (+ bias, ReLU).  ws holds [flag 4 B | dbg 4 B | pad to 256][packed B].  The kernel is skipped
-// on the device when B holds Inf/NaN (flag set by the packer): the caller then runs the gather path
-// conditionally on the same flag.
-int launch_tc_forward(const TcStore& st, const float* B, long long ldb, int N, float* C, long long ldc,
-                      const float* bias, unsigned flags, void* ws, size_t ws_bytes, int nt, cudaStream_t s) {
-  if (st.M == 0 || N == 0) return B200_OK;
+template <int KIND>
+static int tc_launch(const TcStore& st, const int* row_ptr, const int* col, const float* val, const float* B,
+                     long long ldb, int N, float* C, long long ldc, const float* bias, unsigned flags, void* ws, int nt,
+                     cudaStream_t s) {
   const int sms = device_sm_count();
-  if (nt <= 0) nt = tc_pick_nt(st.MB, N, sms);
-  const int terms_opt = options().tc_terms, split_opt = options().tc_split_acc;
-  if (ws_bytes < tc_pack_b_bytes(st.K, N, nt)) {
-    set_error("block-dense path: workspace too small");
-    return B200_ERR_INVALID;
-  }
-  int* flag = reinterpret_cast<int*>(ws);
-  unsigned char* b_pack = reinterpret_cast<unsigned char*>(ws) + 256;
+  int* ctl = reinterpret_cast<int*>(ws);  // zero between launches (the kernel re-arms it on exit)
   const int NB = (N + nt - 1) / nt, NG = NB * (nt / 8);
-  B200_CUDA_OK(cudaMemsetAsync(flag, 0, 8, s));
-  {
-    const int total = st.KT * NG;
-    const int blocks = std::min((total + 7) / 8, sms * 8);
-    if (flags & 1u) tc_pack_b_kernel<true><<<blocks, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, flag);
-    else tc_pack_b_kernel<false><<<blocks, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, flag);
+  uint32_t* colmax = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + 256);
+  unsigned char* b_pack = reinterpret_cast<unsigned char*>(ws) + 256 + tc_colmax_bytes(NG * 8);
+  const bool bt = (flags & 1u) != 0;
+  const int total = st.KT * NG;
+  const int blocks = std::min((total + 7) / 8, sms * 8);
+  if (KIND == KIND_F16 && NG >= sms) {  // wide operand: column maxima and packing in one launch
+    if (bt) tc_prepack_b_kernel<true><<<NG, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
+    else tc_prepack_b_kernel<false><<<NG, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
+    B200_LAUNCH_OK("tc_prepack_b_kernel");
+  } else {
+    if (KIND == KIND_F16) {
+      B200_CUDA_OK(cudaMemsetAsync(colmax, 0, tc_colmax_bytes(NG * 8), s));
+      if (bt) {
+        tc_colmax_kernel<true><<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(B, ldb, st.K, N, colmax, ctl);
+      } else {
+        dim3 grid((unsigned)((N + 255) / 256),
+                  (unsigned)std::max(1, std::min(st.K, (sms * 8) / std::max(1, (N + 255) / 256))));
+        tc_colmax_kernel<false><<<grid, 256, 0, s>>>(B, ldb, st.K, N, colmax, ctl);
+      }
+      B200_LAUNCH_OK("tc_colmax_kernel");
+    }
+    if (bt) tc_pack_b_kernel<KIND, true><<<blocks, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
+    else tc_pack_b_kernel<KIND, false><<<blocks, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
     B200_LAUNCH_OK("tc_pack_b_kernel");
   }
   TcParams p{};
   p.a_tiles = st.tiles; p.blk_ptr = st.blk_ptr; p.blk_kt = st.blk_kt;
   p.b_pack = b_pack; p.NG = NG;
   p.C = C; p.ldc = ldc; p.M = st.M; p.N = N; p.bias = bias; p.flags = flags;
+  p.row_scale = st.row_scale; p.colmax = colmax;
   p.MB = st.MB; p.NB = NB; p.Nt = nt;
-  p.split_acc = split_opt;
-  p.terms = terms_opt;
-  p.skip_if = flag; p.dbg = flag + 1;
+  p.chunk = std::max(1, options().tc_chunk);
+  p.terms = options().tc_terms;
+  p.ctl = ctl;
+  p.row_ptr = row_ptr; p.col = col; p.val = val; p.B = B;
+  p.b_sk = bt ? 1 : ldb; p.b_sn = bt ? ldb : 1;
   const int stage_bytes = A_TILE + nt * 256;
   p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes));
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
@@ -626,13 +873,29 @@ int launch_tc_forward(const TcStore& st, const float* B, long long ldb, int N, f
   int dev = 0;
   B200_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    B200_CUDA_OK(cudaFuncSetAttribute(tc_spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(tc_spmm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev & 63] = true;
   }
   const int grid = std::min(sms, st.MB * NB);
-  tc_spmm_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+  tc_spmm_kernel<KIND><<<grid, TC_THREADS, smem, s>>>(p);
   B200_LAUNCH_OK("tc_spmm_kernel");
   return B200_OK;
+}
+
+// C = A_tiles * B (+ bias, ReLU).  ws: the plan's packed-operand workspace, its first 256 bytes zeroed once when
+// it was allocated.  When the packer finds Inf/NaN in B the same launch computes C in CSR order instead.
+int launch_tc_forward(const TcStore& st, const int* row_ptr, const int* col, const float* val, const float* B,
+                      long long ldb, int N, float* C, long long ldc, const float* bias, unsigned flags, void* ws,
+                      size_t ws_bytes, int nt, cudaStream_t s) {
+  if (st.M == 0 || N == 0) return B200_OK;
+  if (nt <= 0) nt = tc_pick_nt(st.MB, N, device_sm_count());
+  if (ws_bytes < tc_pack_b_bytes(st.K, N, nt, st.kind)) {
+    set_error("block-dense path: workspace too small");
+    return B200_ERR_INVALID;
+  }
+  return st.kind == KIND_F16
+             ? tc_launch<KIND_F16>(st, row_ptr, col, val, B, ldb, N, C, ldc, bias, flags, ws, nt, s)
+             : tc_launch<KIND_TF32>(st, row_ptr, col, val, B, ldb, N, C, ldc, bias, flags, ws, nt, s);
 }
 
 }  // namespace b200

@@ -169,14 +169,27 @@ class cublasTransabMM(InplaceFunction):
 class CsrMatrix:
     '''Device CSR (int32 indices, fp32 values) plus the lazily built, cached transpose.'''
 
-    __slots__ = ('crow', 'col', 'val', 'shape', '_t', '_key', '_val_key')
+    __slots__ = ('crow', 'col', 'val', 'shape', '_t', '_key', '_val_key', '_plan', 'persistent')
 
-    def __init__(self, crow, col, val, shape, key=None):
+    def __init__(self, crow, col, val, shape, key=None, persistent=False):
         self.crow, self.col, self.val = crow, col, val
         self.shape = (int(shape[0]), int(shape[1]))
         self._t = None
         self._key = key
         self._val_key = None
+        self._plan = None
+        # True for operands that live across calls (a CSR tensor cached on the tensor object, a layer's weight):
+        # they get an inspected plan (custom_mm.Plan) — cached task boundaries and transposed CSR, and the densified
+        # tiles of the block-dense tensor-core path.  One-shot conversions of dense operands stay plan-less.
+        self.persistent = persistent
+
+    def plan(self):
+        '''The inspected plan of this operand (inspect once, execute many: the reference's
+        cusparse_inspect / cusparse_mmul_opt pair, src/custom_mm.cpp:236-281, without the string registry).'''
+        if self._plan is None or self._plan[1] != self.val.data_ptr():
+            self._plan = (custom_mm.Plan(self.crow, self.col, self.val, self.shape[0], self.shape[1]),
+                          self.val.data_ptr())
+        return self._plan[0]
 
     @property
     def nnz(self):
@@ -196,10 +209,13 @@ class CsrMatrix:
 
     def refresh_values(self, val):
         '''New values on the same pattern: the cached transpose is re-gathered, not rebuilt.'''
+        same_storage = val.data_ptr() == self.val.data_ptr()
         self.val = val
         if self._t is not None:
             t, perm = self._t
             t.val = custom_mm.gather(val, perm)
+        if self._plan is not None and same_storage:
+            self._plan[0].values_updated()  # else: plan() rebuilds on the new storage
 
     def refresh_values_if_changed(self, values):
         '''Parameter-backed values (cusparseLinear): re-gather the transpose only after an update.'''
@@ -238,6 +254,7 @@ def as_csr(a) -> CsrMatrix:
                       a.values().to(torch.float32).contiguous(), a.shape, key)
         try:
             a._b200_csr = m
+            m.persistent = True  # remembered on the tensor: worth inspecting
         except Exception:
             pass
         return m
@@ -266,6 +283,8 @@ def _spmm_2d(a, b: torch.Tensor, mm_op) -> torch.Tensor:
     if b.stride(-1) != 1:
         b = b.contiguous()
     c = torch.empty(m.shape[0], b.shape[1], device=b.device, dtype=torch.float32)
+    if m.persistent and mm_op is custom_mm.cusparse_mmul and m.nnz > 0:
+        return m.plan().forward(b, c)  # the engine's own op on an inspected operand
     return mm_op(*m.properties(), b, c)
 
 
@@ -342,13 +361,21 @@ def _backward(m1, m2, grad_output, need1, need2, mm_op):
 
     sparse_in = _is_sparse(m1)
     csr = as_csr(m1)
+    planned = csr.persistent and mm_op is custom_mm.cusparse_mmul and csr.nnz > 0
     if need2:
         # grad_b = A^T @ grad_C : SpMM over the cached transposed CSR
-        grad_m2 = _spmm_2d(csr.transposed(), grad_output, mm_op)
+        if planned:
+            grad_m2 = csr.plan().backward_B(grad_output, torch.empty(csr.shape[1], grad_output.shape[1],
+                                                                      device=grad_output.device, dtype=torch.float32))
+        else:
+            grad_m2 = _spmm_2d(csr.transposed(), grad_output, mm_op)
     if need1:
         if sparse_in or masked_dense_grad:
-            dval = custom_mm.sddmm(csr.crow, csr.col, csr.shape[0], csr.shape[1], grad_output,
-                                   m2.to(torch.float32).contiguous())
+            if planned:
+                dval = csr.plan().backward_A(grad_output, m2.to(torch.float32).contiguous())
+            else:
+                dval = custom_mm.sddmm(csr.crow, csr.col, csr.shape[0], csr.shape[1], grad_output,
+                                       m2.to(torch.float32).contiguous())
             if sparse_in:
                 grad_m1 = torch.sparse_csr_tensor(m1.crow_indices(), m1.col_indices(), dval, size=m1.shape)
             else:

@@ -53,8 +53,9 @@ def test_reference_forward_shapes(mods, i, op):
     assert custom_mm.kernel_launch_count() > n0, "the CUDA engine did not run"
     expected = (a.double() @ b.double()).float()
     assert torch.allclose(expected, ours, rtol=1e-5, atol=1e-7)
-    ours_dense_in = getattr(matmuls, op).apply(a, b)  # dense `a`: converted on the device
-    assert torch.equal(ours, ours_dense_in)
+    ours_dense_in = getattr(matmuls, op).apply(a, b)  # dense `a`: converted on the device, plan-less gather kernels
+    # (a CSR tensor is inspected and may take the block-dense tensor-core tiles: same tolerance, other rounding)
+    assert torch.allclose(expected, ours_dense_in, rtol=1e-5, atol=1e-7)
 
 
 def test_dense_to_csr_matches_torch_bit_for_bit(mods):
@@ -227,6 +228,77 @@ def test_fc_layer_like_the_reference_benchmark(mods):
     mask = fc1.dense_weight() != 0
     assert float((got - gw1 * mask).abs().max() / gw1.abs().max()) <= 1e-5
     assert float((fc1.bias.grad.double() - gh.sum(0)).abs().max() / gh.sum(0).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("tc_mode", [0, 2])
+def test_fc_layer_fused_relu_both_paths(mods, tc_mode):
+    """cusparseLinear(activation='relu') on the gather kernels (tc_mode 0: explicit transposes, bias + ReLU fused into
+    the kernels' store) and on the block-dense tensor-core tiles (tc_mode 2: activations read and written as
+    [tokens, features], no transposed copies): forward, dx, dvalues, dbias against fp64."""
+    torch, custom_mm, _ = mods
+    from matrix_multiplication_b200.layers import cusparseLinear
+    custom_mm.set_option("tc_mode", tc_mode)
+    try:
+        torch.manual_seed(6)
+        x = torch.randn(200, 300, device="cuda", requires_grad=True)
+        fc = cusparseLinear(300, 260, sparsity=0.85, seed=3, activation="relu").cuda()
+        with torch.no_grad():
+            fc.bias.copy_(torch.randn(260, device="cuda") * 0.1)
+        y = fc(x)
+        assert fc.csr().plan().last_path() == (1 if tc_mode == 2 else 0)
+        w = fc.dense_weight().double()
+        pre = x.detach().double() @ w.t() + fc.bias.detach().double()
+        ref = pre.clamp_min(0)
+        assert float((y.double() - ref).abs().max() / ref.abs().max()) <= 1e-5
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        g = gy.double() * (pre > 0)
+        assert float((x.grad.double() - g @ w).abs().max() / (g @ w).abs().max()) <= 1e-5
+        gw = g.t() @ x.detach().double()
+        mask = fc.dense_weight() != 0
+        assert float((fc.dense_weight_grad().double() - gw * mask).abs().max() / gw.abs().max()) <= 1e-5
+        assert float((fc.bias.grad.double() - g.sum(0)).abs().max() / g.sum(0).abs().max()) <= 1e-5
+        # in-place update of the values (an optimizer step): the next forward sees them, on both plan sides
+        with torch.no_grad():
+            fc.values.mul_(0.5)
+        y2 = fc(x.detach())
+        ref2 = (x.detach().double() @ (w * 0.5).t() + fc.bias.detach().double()).clamp_min(0)
+        assert float((y2.double() - ref2).abs().max() / ref2.abs().max()) <= 1e-5
+    finally:
+        custom_mm.set_option("tc_mode", 1)
+
+
+def test_fc_layer_loads_the_reference_layers_dense_weight(mods):
+    torch, _, _ = mods
+    from matrix_multiplication_b200.layers import cusparseLinear
+    fc = cusparseLinear(64, 32, sparsity=0.8, seed=1).cuda()
+    w = fc.dense_weight() * 3.0
+    fc2 = cusparseLinear(64, 32, sparsity=0.8, seed=1).cuda()
+    fc2.load_state_dict({"weight": w, "bias": torch.ones(32)})   # keys of benchmarks/cusparse_fc_layer.py:17-21
+    assert torch.equal(fc2.dense_weight(), w) and bool((fc2.bias == 1).all())
+    with pytest.raises(RuntimeError):
+        fc2.load_state_dict({"weight": torch.ones(32, 64), "bias": torch.ones(32)})  # a different pattern
+
+
+def test_cusparsemm_on_a_csr_tensor_uses_the_inspected_plan(mods):
+    """cusparseMM.apply on a CSR tensor: the operand is inspected once (plan cached on the tensor) and a dense-enough
+    one runs on the tensor-core tiles; forward and both gradients against fp64."""
+    torch, custom_mm, matmuls = mods
+    torch.manual_seed(7)
+    a = (torch.rand(384, 256, device="cuda") * (torch.rand(384, 256, device="cuda") < 0.2)).to_sparse_csr()
+    b = torch.rand(256, 96, device="cuda", requires_grad=True)
+    a.requires_grad_(True)
+    out = matmuls.cusparseMM.apply(a, b)
+    assert matmuls.as_csr(a).plan().last_path() == 1
+    ad = a.detach().to_dense().double()
+    ref = ad @ b.detach().double()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) <= 1e-5
+    g = torch.rand_like(out)
+    out.backward(g)
+    gb = ad.t() @ g.double()
+    assert float((b.grad.double() - gb).abs().max() / gb.abs().max()) <= 1e-5
+    ga = (g.double() @ b.detach().double().t()) * (ad != 0)
+    assert float((a.grad.to_dense().double() - ga).abs().max() / ga.abs().max()) <= 1e-5
 
 
 def test_batched_product_is_one_launch(mods):

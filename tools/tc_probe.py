@@ -97,7 +97,7 @@ def run_case(name, A, B, flags=OP_FORCE_TC, bias=None, opts=None, timing=False, 
     except Exception as e:  # noqa: BLE001
         rec["error"] = repr(e)
     for k in (opts or {}):
-        capi.set_option(k, {"tc_terms": 7, "tc_split_acc": 0, "tc_nt": 0, "tc_mode": 1}.get(k, 0))
+        capi.set_option(k, {"tc_terms": 7, "tc_chunk": 4, "tc_nt": 0, "tc_mode": 1, "tc_kind": 1}.get(k, 0))
     plan.close()
     out(**rec)
     return rec
@@ -110,63 +110,92 @@ def main():
     args = ap.parse_args()
     out(device=torch.cuda.get_device_name(0), sms=capi.smoke())
 
+    kinds = (0, 1)
     # 1. layout: A = first 32 columns identity, B small exact values -> C[r] = B[r] for r < 32, 0 elsewhere
     A = torch.zeros(128, 32, device=dev)
     A[torch.arange(32), torch.arange(32)] = 1.0
     B = (torch.arange(32, device=dev)[:, None] + torch.arange(32, device=dev)[None, :] / 64.0).float()
-    run_case("layout_identity", A, B, opts={"tc_terms": 1})
-    run_case("layout_identity_all_terms", A, B)
+    for kind in kinds:
+        run_case(f"layout_identity_k{kind}", A, B, opts={"tc_terms": 1, "tc_kind": kind})
     # permutation-like A exercising every (row, k) swizzle position
-    A = torch.zeros(128, 64, device=dev)
+    A = torch.zeros(128, 128, device=dev)
     r = torch.arange(128, device=dev)
-    A[r, (r * 7 + 3) % 64] = ((r % 5) + 1).float()
-    B = (torch.arange(64, device=dev)[:, None] * 2 + torch.arange(64, device=dev)[None, :] / 32.0).float()
-    run_case("layout_perm", A, B, opts={"tc_terms": 1})
+    A[r, (r * 7 + 3) % 128] = ((r % 5) + 1).float()
+    B = (torch.arange(128, device=dev)[:, None] * 2 + torch.arange(64, device=dev)[None, :] / 32.0).float()
+    for kind in kinds:
+        run_case(f"layout_perm_k{kind}", A, B, opts={"tc_kind": kind})
 
     # 2. accuracy of the split
     A = rand_sparse(128, 64, 0.5)
     B = torch.randn(64, 64, device=dev)
-    run_case("rand_hi_only", A, B, opts={"tc_terms": 1})
-    run_case("rand_3x", A, B)
-    run_case("rand_3x_split", A, B, opts={"tc_split_acc": 1})
+    for kind in kinds:
+        run_case(f"rand_hi_only_k{kind}", A, B, opts={"tc_terms": 1, "tc_kind": kind})
+        run_case(f"rand_3x_k{kind}", A, B, opts={"tc_kind": kind})
     # 3. ragged edges, several row blocks / k tiles / n blocks, every tile width
     A = rand_sparse(300, 200, 0.3, seed=1)
     B = torch.randn(200, 100, device=dev)
-    for nt in (32, 64, 96, 128, 160, 192, 224, 256):
-        run_case(f"ragged_nt{nt}", A, B, opts={"tc_nt": nt})
+    for kind in kinds:
+        for nt in (64, 128, 192, 256):
+            run_case(f"ragged_nt{nt}_k{kind}", A, B, opts={"tc_nt": nt, "tc_kind": kind})
     A = rand_sparse(1000, 1000, 0.1, seed=2)
     B = torch.randn(1000, 777, device=dev)
-    run_case("ragged_1000", A, B)
     bias = torch.randn(1000, device=dev)
-    run_case("bias_relu", A, B, flags=OP_FORCE_TC | OP_RELU, bias=bias)
-    run_case("bt", A, B, bt=True)
-    run_case("ct", A, B, ct=True)
-    run_case("bt_ct_bias_relu", A, B, flags=OP_FORCE_TC | OP_RELU, bias=bias, bt=True, ct=True)
-    # empty row blocks and empty k tiles
     A2 = A.clone()
     A2[128:384] = 0
     A2[:, 64:256] = 0
-    run_case("empty_blocks", A2, B)
-    # non-finite dense operand -> CSR-order fallback on the device
     B2 = B.clone()
     B2[5, 7] = float("inf")
     B2[9, 3] = float("nan")
-    ref = torch.zeros(1000, 777, device=dev, dtype=torch.float64)
-    Ad = A.double()
-    Bd = B2.double()
-    Bd0 = torch.where(torch.isfinite(Bd), Bd, torch.zeros_like(Bd))
-    ref = Ad @ Bd0
-    rec = run_case("nonfinite_fallback", A, B2, ref64=ref)
+    # wide dynamic range: rows of A and columns of B spanning 2^+-40, and a tiny-but-relevant element pairing
+    rsc = torch.exp2(torch.linspace(-40, 40, 1000, device=dev)).float()
+    csc = torch.exp2(torch.linspace(30, -30, 777, device=dev)).float()
+    A3 = A * rsc[:, None]
+    B3 = B * csc[None, :]
+    A4 = A.clone()
+    B4 = B.clone()
+    A4[:, 17] = A4[:, 17] * 1e6
+    B4[17, :] = B4[17, :] * 1e-6
+    for kind in kinds:
+        o = {"tc_kind": kind}
+        run_case(f"ragged_1000_k{kind}", A, B, opts=o)
+        run_case(f"bias_relu_k{kind}", A, B, flags=OP_FORCE_TC | OP_RELU, bias=bias, opts=o)
+        run_case(f"bt_k{kind}", A, B, bt=True, opts=o)
+        run_case(f"ct_k{kind}", A, B, ct=True, opts=o)
+        run_case(f"bt_ct_bias_relu_k{kind}", A, B, flags=OP_FORCE_TC | OP_RELU, bias=bias, bt=True, ct=True, opts=o)
+        run_case(f"empty_blocks_k{kind}", A2, B, opts=o)
+        run_case(f"range_rows_cols_k{kind}", A3, B3, opts=o)
+        run_case(f"range_pairing_k{kind}", A4, B4, opts=o)
+        # non-finite dense operand -> CSR-order fallback on the device: must equal the gather kernels' result
+        crow, col, val = make_csr(A)
+        pl = capi.Plan(crow, col, val, A.shape)
+        Cg = torch.empty(1000, 777, device=dev)
+        pl.forward_ex(B2, Cg, flags=OP_NO_TC)
+        capi.set_option("tc_kind", kind)
+        Ct = torch.empty(1000, 777, device=dev)
+        pl.forward_ex(B2, Ct, flags=OP_FORCE_TC)
+        torch.cuda.synchronize()
+        capi.set_option("tc_kind", 1)
+        same_nan = bool((torch.isnan(Cg) == torch.isnan(Ct)).all())
+        fin = torch.isfinite(Cg)
+        out(case=f"nonfinite_fallback_k{kind}", same_nan_pattern=same_nan, nan=int(torch.isnan(Ct).sum()),
+            inf=int(torch.isinf(Ct).sum()), max_diff_finite=float((Cg[fin] - Ct[fin]).abs().max()))
+        pl.close()
 
     # 4. accumulate rounding: long K, positive data
     A = rand_sparse(256, 16384, 0.5, signed=False, seed=3)
     B = torch.rand(16384, 256, device=dev)
     ref = A.double() @ B.double()
-    run_case("longk_pos", A, B, ref64=ref)
-    run_case("longk_pos_split", A, B, opts={"tc_split_acc": 1, "tc_nt": 128}, ref64=ref)
-    run_case("longk_pos_hi", A, B, opts={"tc_terms": 1}, ref64=ref)
-    run_case("longk_pos_gather", A, B, flags=OP_NO_TC, ref64=ref)
+    for kind in kinds:
+        for ch in (1, 2, 4, 8, 16, 1000):
+            run_case(f"longk_pos_k{kind}_chunk{ch}", A, B, opts={"tc_chunk": ch, "tc_kind": kind}, ref64=ref, timing=True)
+    run_case("longk_pos_gather", A, B, flags=OP_NO_TC, ref64=ref, timing=True)
     out(case="longk_pos_torch_fp32", rel_err=rel_err(A @ B, ref))
+    As = rand_sparse(256, 16384, 0.5, signed=True, seed=3)
+    Bs = torch.randn(16384, 256, device=dev)
+    ref = As.double() @ Bs.double()
+    for kind in kinds:
+        for ch in (4, 1000):
+            run_case(f"longk_signed_k{kind}_chunk{ch}", As, Bs, opts={"tc_chunk": ch, "tc_kind": kind}, ref64=ref)
     if args.quick:
         return
 
@@ -176,17 +205,18 @@ def main():
         B = torch.rand(K, 4096, device=dev)
         ref = A.double() @ B.double()
         run_case(f"c3_{M}x{K}_gather", A, B, flags=OP_NO_TC, timing=True, ref64=ref)
-        for nt in (0, 64, 128, 192, 256):
-            run_case(f"c3_{M}x{K}_nt{nt}", A, B, opts={"tc_nt": nt}, timing=True, ref64=ref)
-        run_case(f"c3_{M}x{K}_split128", A, B, opts={"tc_nt": 128, "tc_split_acc": 1}, timing=True, ref64=ref)
-        run_case(f"c3_{M}x{K}_hi_only", A, B, opts={"tc_terms": 1}, timing=True, ref64=ref)
-        run_case(f"c3_{M}x{K}_bt_ct", A, B, timing=True, ref64=ref, bt=True, ct=True)
-        Ad = A
-        torch.backends.cuda.matmul.allow_tf32 = False
-        out(case=f"c3_{M}x{K}_torch_fp32", ms=time_ms(lambda: torch.mm(Ad, B)))
+        for kind in kinds:
+            for nt in (0, 128, 192, 256):
+                run_case(f"c3_{M}x{K}_k{kind}_nt{nt}", A, B, opts={"tc_nt": nt, "tc_kind": kind}, timing=True, ref64=ref)
+            for ch in (2, 8):
+                run_case(f"c3_{M}x{K}_k{kind}_chunk{ch}", A, B, opts={"tc_chunk": ch, "tc_kind": kind}, timing=True, ref64=ref)
+            run_case(f"c3_{M}x{K}_k{kind}_hi_only", A, B, opts={"tc_terms": 1, "tc_kind": kind}, timing=True, ref64=ref)
+            run_case(f"c3_{M}x{K}_k{kind}_bt_ct", A, B, opts={"tc_kind": kind}, timing=True, ref64=ref, bt=True, ct=True)
         torch.backends.cuda.matmul.allow_tf32 = True
-        out(case=f"c3_{M}x{K}_torch_tf32", ms=time_ms(lambda: torch.mm(Ad, B)), rel_err=rel_err(torch.mm(Ad, B), ref))
+        out(case=f"c3_{M}x{K}_torch_tf32", ms=time_ms(lambda: torch.mm(A, B)), rel_err=rel_err(torch.mm(A, B), ref))
         torch.backends.cuda.matmul.allow_tf32 = False
+        Ah, Bh = A.half(), B.half()
+        out(case=f"c3_{M}x{K}_torch_fp16", ms=time_ms(lambda: torch.mm(Ah, Bh)))
 
     # 6. config 5 points
     if args.big:
@@ -194,14 +224,10 @@ def main():
             A = rand_sparse(16384, 16384, 1 - sparsity, signed=False, seed=5)
             for N in (64, 256):
                 B = torch.rand(16384, N, device=dev)
-                ref = None
-                # row-sampled fp64 reference (full fp64 product of 16k^2 x 256 is fine on the GPU too)
                 ref = A.double() @ B.double()
                 run_case(f"c5_{sparsity}_{N}_gather", A, B, flags=OP_NO_TC, timing=True, ref64=ref)
-                run_case(f"c5_{sparsity}_{N}_tc", A, B, timing=True, ref64=ref)
-                if N == 256:
-                    run_case(f"c5_{sparsity}_{N}_tc_split", A, B, opts={"tc_nt": 128, "tc_split_acc": 1}, timing=True,
-                             ref64=ref)
+                for kind in kinds:
+                    run_case(f"c5_{sparsity}_{N}_tc_k{kind}", A, B, opts={"tc_kind": kind}, timing=True, ref64=ref)
                 torch.backends.cuda.matmul.allow_tf32 = False
                 out(case=f"c5_{sparsity}_{N}_torch_fp32", ms=time_ms(lambda: torch.mm(A, B), iters=5))
             del A
