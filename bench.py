@@ -280,6 +280,30 @@ def max_over_ranks(x: float, dist) -> float:
     return float(t.item())
 
 
+def all_ranks(x: float, dist):
+    """x of every rank, as a list (rank order)."""
+    if dist is None:
+        return [x]
+    import torch
+    t = torch.zeros(dist.get_world_size(), dtype=torch.float64, device="cuda")
+    t[dist.get_rank()] = x
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]
+
+
+def committed_traffic():
+    """dram bytes per launch of the dominant kernel, parsed from the committed ncu --set full capture summary
+    (profiles/*_ncu_fwd_c4.json, written by tools/ncu_traffic.py from the .ncu-rep)."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r*_ncu_fwd_c4.json")):
+        try:
+            d = json.loads(f.read_text())
+            best = (float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), f.name)
+        except Exception:
+            pass
+    return best
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -288,6 +312,67 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# the other BASELINE configs, compact (parity cases, not the headline): forward on the path the plan picks, next to the
+# kernel-fair cuSPARSE call on the same operands.  Cold = 256 MB L2 flush before every timed launch.
+# ---------------------------------------------------------------------------------------------------
+def run_config_block(dev, peak):
+    import torch
+    from matrix_multiplication_b200 import capi, synthetic
+    from tools import cusparse_fair
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush_buf.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    cases = [("c1 1024^2 @90% x64", "c1", None), ("c3 fc1 3072x768 @90% x4096", "c3", None),
+             ("c5 16384^2 @90% x16", "c5:0.9:16", None), ("c5 16384^2 @90% x64", "c5:0.9:64", None),
+             ("c5 16384^2 @90% x256", "c5:0.9:256", None), ("c5 16384^2 @99% x64", "c5:0.99:64", None)]
+    rows = []
+    t_start = time.time()
+    for label, name, scale in cases:
+        if time.time() - t_start > 75:  # keep the default run short
+            rows.append({"config": label, "skipped": "time budget"})
+            continue
+        w = make_workload(name, scale)
+        M, K = w["shape"]
+        N, nnz = w["N"], len(w["val"])
+        crow, col, val = (torch.from_numpy(x).to(dev) for x in (w["row_ptr"], w["col"], w["val"]))
+        B = torch.from_numpy(w["B"]).to(dev)
+        C = torch.empty(M, N, device=dev)
+        plan = capi.Plan(crow, col, val, (M, K))
+        plan.forward(B, C)
+        t = timeit(lambda: plan.forward(B, C))
+        by = synthetic.spmm_algorithmic_bytes(M, K, nnz, N)
+        r = {"config": label, "nnz": nnz, "path": ["gather kernels", "tensor-core tiles", "strided"][plan.tc_info()["last_path"]],
+             "fwd_ms": round(t, 5), "gflops": round(2.0 * nnz * N / t / 1e6, 1),
+             "frac_of_hbm_roof": round(by / t / 1e6 / peak, 4)}
+        try:
+            Cf = torch.empty(M, N, device=dev)
+            fair = cusparse_fair.FairSpMM(crow, col, val, (M, K), B, Cf)
+            fair.run()
+            r["cusparse_kernel_fair_ms"] = round(timeit(fair.run), 5)
+            r["speedup"] = round(r["cusparse_kernel_fair_ms"] / t, 2)
+            r["rel_diff_vs_cusparse"] = float((Cf - C).abs().max() / Cf.abs().max().clamp_min(1e-30))
+            fair.close()
+        except Exception as e:
+            r["cusparse_kernel_fair_ms"] = f"failed: {e}"
+        plan.close()
+        rows.append(r)
+        del crow, col, val, B, C
+        torch.cuda.empty_cache()
+    return rows
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -343,7 +428,8 @@ def run_ours(args):
     with clk:  # clocks are sampled across all timed regions
         dev_ms, wall_ms = timed_region(step_resident, args.steps, args.warmup, dist, flush)
     launches = capi.kernel_launch_count() - n0
-    kern_ms = dev_ms  # this rank's own device time = its spmm_flat_kernel (+ fix-up) launches
+    kern_ms = dev_ms  # this rank's own device time = its spmm_flat_kernel launches (one per step)
+    per_rank_ms = all_ranks(dev_ms / args.steps, dist)
     dev_ms = max_over_ranks(dev_ms, dist)
     ms_per_step = dev_ms / args.steps
     gathered_ms = None
@@ -377,6 +463,56 @@ def run_ours(args):
                 del sym
             except Exception as e:  # symmetric memory is plumbing that may be unavailable on a box
                 fused[mode] = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
+
+    # ---- multi-GPU phases the north_star names (all ranks take part): B broadcast, C gathered to one rank, and the
+    # row-sharded backward (grad_A local, grad_B = reduce-scatter of the ranks' partial A_g^T G_g) ----------------
+    mg_phases = None
+    if world > 1:
+        mg_phases = {}
+        Bb = torch.empty_like(B)
+        if rank == 0:
+            Bb.copy_(B)
+        ms, _ = timed_region(lambda: dist.broadcast(Bb, src=0), args.steps, args.warmup, dist, None)
+        ms = max_over_ranks(ms, dist) / args.steps
+        mg_phases["B_broadcast_from_rank0_ms"] = round(ms, 5)
+        mg_phases["B_broadcast_GBs_per_rank_ingress"] = round(K * N * 4 / (ms * 1e-3) / 1e9, 1)
+        del Bb
+        ms, _ = timed_region(lambda: gather.gather_to(0), args.steps, args.warmup, dist, None)
+        ms = max_over_ranks(ms, dist) / args.steps
+        mg_phases["C_gather_to_rank0_ms"] = round(ms, 5)
+        mg_phases["C_gather_rank0_ingress_GBs"] = round((M - (r1 - r0 if rank == 0 else int(bounds[1] - bounds[0]))) * N * 4
+                                                        / (ms * 1e-3) / 1e9, 1)
+        ms, _ = timed_region(lambda: (plan.forward(B, C_local, stream=stream), gather.gather_to(0)), args.steps,
+                             args.warmup, dist, None)
+        mg_phases["forward_plus_gather_to_rank0_ms"] = round(max_over_ranks(ms, dist) / args.steps, 5)
+        if K % world == 0:
+            G_local = torch.rand(r1 - r0, N, device=dev)
+            dA_local = torch.empty(p1 - p0, device=dev)
+            dB_part = torch.empty(K, N, device=dev)
+            dB_mine = torch.empty(K // world, N, device=dev)
+            plan.backward_B(G_local, dB_part, stream=stream)  # builds the transposed shard (inspector time)
+            ga, _ = timed_region(lambda: plan.backward_A(G_local, B, dA_local, stream=stream), args.steps, args.warmup,
+                                 dist, None)
+            gb, _ = timed_region(lambda: plan.backward_B(G_local, dB_part, stream=stream), args.steps, args.warmup, dist,
+                                 None)
+            rs, _ = timed_region(lambda: sharding.reduce_scatter_rows(dB_part, dB_mine, dist), args.steps, args.warmup,
+                                 dist, None)
+
+            def bwd_step():
+                plan.backward_A(G_local, B, dA_local, stream=stream)
+                plan.backward_B(G_local, dB_part, stream=stream)
+                sharding.reduce_scatter_rows(dB_part, dB_mine, dist)
+            bw, _ = timed_region(bwd_step, args.steps, args.warmup, dist, None)
+            ga, gb, rs, bw = (max_over_ranks(x, dist) / args.steps for x in (ga, gb, rs, bw))
+            mg_phases.update({
+                "grad_A_local_sddmm_ms": round(ga, 5), "grad_B_partial_spmm_ms": round(gb, 5),
+                "grad_B_reduce_scatter_ms": round(rs, 5), "backward_step_ms": round(bw, 5),
+                "fwd_bwd_ms": round(ms_per_step + bw, 5),
+                "fwd_bwd_gflops": round(3 * flops(w) / ((ms_per_step + bw) * 1e-3) / 1e9, 1),
+                "what": "grad_A: SDDMM on the shard's pattern (no exchange); grad_B: every rank's [K, N] partial A_g^T G_g "
+                        "then one NCCL reduce-scatter (rank g keeps K/G rows); link bound of the exchange = "
+                        f"{(world - 1) / world * K * N * 4 / 770e9 * 1e3:.3f} ms at 770 GB/s per direction"})
+            del G_local, dA_local, dB_part, dB_mine
 
     # ---- e2e through the public API with host buffers -------------------------------------------------
     a_t = torch.sparse_csr_tensor(crow.long(), col.long(), val, size=(r1 - r0, K))
@@ -499,6 +635,28 @@ def run_ours(args):
         except Exception as e:
             comp["reference_cusparse_mmul_ms"] = f"failed: {e}"
 
+        try:
+            from tools import cusparse_fair
+            Cf = torch.empty(M, N, device=dev)
+            fair = cusparse_fair.FairSpMM(crow, col, val, (M, K), B, Cf, stream=stream)
+            fair.run()
+            ms, _ = timed_region(fair.run, max(3, args.steps // 2), 2, None, flush)
+            comp["cusparse_spmm_alg2_kernel_fair_ms"] = round(ms / max(3, args.steps // 2), 4)
+            comp["cusparse_kernel_fair_what"] = ("cusparseSpMM CSR_ALG2, row-major B/C as the reference calls it "
+                                                 "(src/baseline_mm.cu:186-213), descriptors + buffer + preprocess hoisted")
+            comp["speedup_vs_cusparse_kernel_fair"] = round(comp["cusparse_spmm_alg2_kernel_fair_ms"] / ms_per_step, 3)
+            fair.close()
+            del Cf
+        except Exception as e:
+            comp["cusparse_spmm_alg2_kernel_fair_ms"] = f"failed: {e}"
+
+    configs_block = None
+    if world == 1 and not args.no_configs:
+        try:
+            configs_block = run_config_block(dev, peaks()[0])
+        except Exception as e:  # informational block: never lose the headline line over it
+            configs_block = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     cpu = cpu_baseline(w) if world == 1 and not args.no_cpu else None
     peak, peak_src = peaks()
     # the dominant kernel: spmm_fwd_kernel over this rank's shard (rank 0's shard for the roofline)
@@ -519,7 +677,10 @@ def run_ours(args):
         "effective_gbs": round(algorithmic_bytes(w) / (ms_per_step * 1e-3) / 1e9, 1),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": args.traffic,
-                     "kernel": "spmm_flat_kernel (+ spmm_fixup_kernel)", "kernel_ms": round(k_ms, 5), "algorithmic_bytes": sh_bytes,
+                     "traffic_source": args.traffic_source,
+                     "kernel": "spmm_flat_kernel (single launch: split rows are summed by the last arriving task)",
+                     "kernel_ms": round(k_ms, 5), "kernel_ms_per_rank": [round(x, 5) for x in per_rank_ms],
+                     "algorithmic_bytes": sh_bytes,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
         "e2e": {"value": round(flops(w) / (e2e_ms * 1e-3) / 1e9, 2), "unit": "GFLOP/s",
                 "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": int(M * N * 4),
@@ -538,10 +699,14 @@ def run_ours(args):
     }
     if phases is not None:
         out["phases"] = phases
+    if mg_phases is not None:
+        out["phases"] = mg_phases
+    if configs_block is not None:
+        out["configs"] = configs_block
     if gathered_ms is not None:
         out["gathered"] = {"value": round(flops(w) / (gathered_ms * 1e-3) / 1e9, 2), "unit": "GFLOP/s",
                            "ms_per_step": round(gathered_ms, 5),
-                           "what": "same step + every rank receives all of C (one NCCL broadcast per row block)",
+                           "what": "same step + every rank receives all of C (one grouped NCCL all-gather of unequal row blocks)",
                            "fused_epilogue": fused}
     if cpu is not None:
         out["cpu_baseline"] = cpu
@@ -626,15 +791,19 @@ def main():
     ap.add_argument("--scale", type=int, default=None, help="R-MAT scale (c4) or matrix dimension (c5) override")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-comparators", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact block of the other BASELINE configs")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (b200_set_option)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture "
                          "(default: the committed figure for the default workload on 1 GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.traffic_source = "--traffic" if args.traffic is not None else None
     if args.traffic is None and args.workload == "c4" and args.scale is None and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        # dram__bytes_read.sum + dram__bytes_write.sum of spmm_flat_kernel, profiles/r1_ncu_fwd_c4.md
-        args.traffic = 1.553385e9 + 0.505407e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of spmm_flat_kernel from the committed capture of this workload
+        t = committed_traffic()
+        if t is not None:
+            args.traffic, args.traffic_source = t
     if args.impl == "reference":
         run_reference(args)
     else:

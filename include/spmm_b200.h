@@ -135,6 +135,19 @@ int b200_dense_to_csr_count(const float* d_dense, int64_t M, int64_t K, int64_t 
 int b200_dense_to_csr_fill(const float* d_dense, int64_t M, int64_t K, int64_t ld,
                            const int32_t* d_row_ptr, int32_t* d_col_ind, float* d_val,
                            void* stream);
+/* One pass: count, global prefix (decoupled look-back across CTAs) and fill in ONE kernel — the dense matrix is read
+ * exactly once (the two-phase pair above reads it twice, as cusparseDenseToSparse_analysis + _convert do,
+ * src/baseline_mm.cu:241-258).  The caller provides room for `capacity` non-zeros (M*K always suffices; a known
+ * sparsity gives a tighter bound).  Writes row_ptr[M+1] and the first min(nnz, capacity) entries of col_ind / val.
+ * If h_nnz != NULL the stream is synchronised and nnz returned; nnz > capacity is reported as B200_ERR_INVALID with
+ * *h_nnz set and row_ptr complete, so the caller can allocate exactly and finish with b200_dense_to_csr_fill.
+ * d_scratch: b200_dense_to_csr_onepass_scratch_bytes(M, K) bytes of device memory, 16-byte aligned (tile states of
+ * the look-back); NULL = the library allocates and frees it around the call (and synchronises the stream).
+ * Same bit-exact contract as above. */
+size_t b200_dense_to_csr_onepass_scratch_bytes(int64_t M, int64_t K);
+int b200_dense_to_csr_onepass(const float* d_dense, int64_t M, int64_t K, int64_t ld, int32_t* d_row_ptr,
+                              int32_t* d_col_ind, float* d_val, int64_t capacity, void* d_scratch,
+                              size_t scratch_bytes, int64_t* h_nnz, void* stream);
 /* One-call variant with the reference's ownership (dense_to_csr allocates with
  * cudaMalloc, free_csr releases; src/baseline_mm.cu:218-270). Synchronises. */
 int b200_dense_to_csr_alloc(const float* d_dense, int64_t M, int64_t K, int64_t ld,

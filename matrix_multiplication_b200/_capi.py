@@ -56,6 +56,8 @@ SIGNATURES = {
     "b200_gather_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "b200_dense_to_csr_count": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64p, _vp]),
     "b200_dense_to_csr_fill": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "b200_dense_to_csr_onepass_scratch_bytes": (C.c_size_t, [_i64, _i64]),
+    "b200_dense_to_csr_onepass": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, C.c_size_t, _i64p, _vp]),
     "b200_dense_to_csr_alloc": (C.c_int, [_vp, _i64, _i64, _i64, C.POINTER(_vp), C.POINTER(_vp),
                                           C.POINTER(_vp), _i64p, _vp]),
     "b200_free_csr": (C.c_int, [_vp, _vp, _vp]),
@@ -246,6 +248,28 @@ def spmm_device(crow, col, val, shape, B, Cout, ldb=None, ldc=None, workspace=No
                                             N if ldc is None else ldc, ws_p, ws_n,
                                             C.c_void_p(stream), flags))
     return Cout
+
+
+def dense_to_csr_onepass_device(dense, capacity=None, stream=0):
+    """b200_dense_to_csr_onepass on a 2-D torch CUDA tensor (unit stride in the last dimension).  Returns
+    (crow, col, val, nnz) with col / val holding `capacity` slots (default M*K); raises B200Error (ERR_INVALID, nnz
+    in the message, crow complete) when capacity is too small."""
+    import torch
+    M, K = dense.shape
+    cap = M * K if capacity is None else int(capacity)
+    crow = torch.empty(M + 1, dtype=torch.int32, device=dense.device)
+    col = torch.empty(max(cap, 1), dtype=torch.int32, device=dense.device)
+    val = torch.empty(max(cap, 1), dtype=torch.float32, device=dense.device)
+    nnz = C.c_int64(0)
+    sb = lib().b200_dense_to_csr_onepass_scratch_bytes(M, K)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dense.device)
+    rc = lib().b200_dense_to_csr_onepass(_dp(dense), M, K, dense.stride(0) if M > 1 else max(K, 1), _dp(crow), _dp(col),
+                                         _dp(val), cap, _dp(scratch), sb, C.byref(nnz), C.c_void_p(stream))
+    if rc != OK:
+        err = B200Error(rc, lib().b200_last_error().decode())
+        err.nnz, err.crow = nnz.value, crow
+        raise err
+    return crow, col, val, nnz.value
 
 
 def sddmm_device(crow, col, shape, G, B, out, stream=0):

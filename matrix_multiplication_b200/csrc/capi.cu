@@ -251,6 +251,10 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
+  if (!strcmp(name, "d2c_warps")) {
+    B200_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "d2c_warps must be 0, 2, 4, 8 or 16");
+    options().d2c_warps = (int)value; return B200_OK;
+  }
   if (!strcmp(name, "tc_mode")) { options().tc_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "tc_nt")) {
     B200_REQUIRE(value == 0 || (value % 64 == 0 && value >= 64 && value <= 256), "tc_nt must be 0 or a multiple of 64 up to 256");
@@ -269,6 +273,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "pipeline")) return options().pipeline;
   if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
+  if (!strcmp(name, "d2c_warps")) return options().d2c_warps;
   if (!strcmp(name, "tc_mode")) return options().tc_mode;
   if (!strcmp(name, "tc_nt")) return options().tc_nt;
   if (!strcmp(name, "tc_terms")) return options().tc_terms;
@@ -370,6 +375,61 @@ int b200_dense_to_csr_fill(const float* d_dense, int64_t M, int64_t K, int64_t l
   if (M == 0 || K == 0) return B200_OK;
   B200_REQUIRE(d_dense && d_row_ptr, "null dense / row_ptr");
   return launch_dense_fill(d_dense, (int)M, (int)K, ld, d_row_ptr, d_col_ind, d_val, (cudaStream_t)stream);
+}
+
+size_t b200_dense_to_csr_onepass_scratch_bytes(int64_t M, int64_t K) {
+  if (M <= 0 || K <= 0 || M >= 0x7fffffffLL || K >= 0x7fffffffLL) return 16;
+  return dense_onepass_scratch_bytes((int)M, (int)K);
+}
+
+int b200_dense_to_csr_onepass(const float* d_dense, int64_t M, int64_t K, int64_t ld, int32_t* d_row_ptr,
+                              int32_t* d_col_ind, float* d_val, int64_t capacity, void* d_scratch,
+                              size_t scratch_bytes, int64_t* h_nnz, void* stream) {
+  B200_REQUIRE(M >= 0 && K >= 0 && M < 0x7fffffffLL && K < 0x7fffffffLL, "dimension out of range");
+  B200_REQUIRE(ld >= K, "leading dimension smaller than K");
+  B200_REQUIRE(d_row_ptr != nullptr && capacity >= 0, "null row_ptr / negative capacity");
+  B200_REQUIRE(capacity == 0 || (d_col_ind != nullptr && d_val != nullptr), "null col / val");
+  B200_REQUIRE(M == 0 || K == 0 || d_dense != nullptr, "null dense");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!dense_onepass_supported(d_dense, (int)M, (int)K, ld)) {
+    // unaligned rows or very narrow matrices: the two-pass kernels (the matrix is small or oddly shaped anyway)
+    int64_t n = 0;
+    int rc = b200_dense_to_csr_count(d_dense, M, K, ld, d_row_ptr, &n, stream);
+    if (rc) return rc;
+    if (h_nnz) *h_nnz = n;
+    if (n > capacity) {
+      set_error("capacity %lld too small for %lld non-zeros (row_ptr is complete)", (long long)capacity, (long long)n);
+      return B200_ERR_INVALID;
+    }
+    return b200_dense_to_csr_fill(d_dense, M, K, ld, d_row_ptr, d_col_ind, d_val, stream);
+  }
+  const size_t need = dense_onepass_scratch_bytes((int)M, (int)K);
+  void* scratch = d_scratch;
+  DevBuf own;
+  if (scratch == nullptr) {  // convenience: callers on a hot path pass their own scratch (no allocation here)
+    int rc = own.alloc(need);
+    if (rc) return rc;
+    scratch = own.p;
+  } else {
+    B200_REQUIRE(scratch_bytes >= need, "one-pass scratch too small (b200_dense_to_csr_onepass_scratch_bytes)");
+    B200_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, "one-pass scratch must be 16-byte aligned");
+  }
+  int rc = launch_dense_onepass(d_dense, (int)M, (int)K, ld, d_row_ptr, d_col_ind, d_val, capacity, scratch, s);
+  int n = 0;
+  if (rc == B200_OK && (h_nnz || own.p)) {
+    B200_CUDA_OK(cudaMemcpyAsync(&n, d_row_ptr + M, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));  // (also keeps a library-owned scratch alive until the kernel is done)
+  }
+  if (rc) return rc;
+  if (h_nnz) {
+    *h_nnz = n;
+    if (n > capacity) {
+      set_error("capacity %lld too small for %lld non-zeros (row_ptr is complete: allocate and call b200_dense_to_csr_fill)",
+                (long long)capacity, (long long)n);
+      return B200_ERR_INVALID;
+    }
+  }
+  return B200_OK;
 }
 
 int b200_dense_to_csr_alloc(const float* d_dense, int64_t M, int64_t K, int64_t ld, float** d_val,

@@ -52,6 +52,7 @@ struct Options {
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
   int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
                            // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
+  int d2c_warps = 0;       // dense->CSR one-pass tile size in warps (2, 4, 8, 16; 0 = default 4)
   // block-dense tensor-core path (tc_gemm.cu)
   int tc_mode = 1;         // 0 = never, 1 = auto (density / N rule), 2 = whenever the shape allows it
   int tc_nt = 0;           // tile width override (multiple of 32, <= 256); 0 = auto
@@ -286,6 +287,10 @@ int launch_gather(const float* src, const int* perm, long long n, float* dst, cu
 int launch_dense_count(const float* dense, int M, int K, long long ld, int* row_ptr, cudaStream_t s);
 int launch_dense_fill(const float* dense, int M, int K, long long ld, const int* row_ptr, int* col,
                       float* val, cudaStream_t s);
+size_t dense_onepass_scratch_bytes(int M, int K);
+bool dense_onepass_supported(const float* dense, int M, int K, long long ld);
+int launch_dense_onepass(const float* dense, int M, int K, long long ld, int* row_ptr, int* col, float* val,
+                         long long capacity, void* scratch, cudaStream_t s);
 int launch_row_stats(const int* row_ptr, int M, int* d_out2 /* max_len, empty */, cudaStream_t s);
 int launch_block_diag(const int* row_ptr, int* col, int rows, int M, int K, cudaStream_t s);
 

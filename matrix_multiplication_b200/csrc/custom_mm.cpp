@@ -292,13 +292,31 @@ void tiledspmm_clean() {
 }
 
 // ---- engine extras used by matmuls.py (not in the reference's module) ------------------------
-std::vector<torch::Tensor> dense_to_csr(torch::Tensor dense) {
+// dense -> CSR.  Default: the two-phase pair (count, exact allocation, fill) — measured faster than the one-pass
+// kernel on a B200 (16384^2: 0.42-0.70 ms vs 0.86-1.3 ms, profiles/r2_dense2csr.md: the cross-CTA look-back of the
+// one-pass kernel stalls its tiles).  set_onepass_max_elems(n) routes matrices of up to n elements through the
+// one-pass kernel (worst-case sized outputs, 8 bytes per dense element; compact = true returns right-sized copies).
+int64_t g_onepass_max_elems = 0;
+std::vector<torch::Tensor> dense_to_csr(torch::Tensor dense, bool compact) {
   check_dense(dense, "dense");
   c10::cuda::CUDAGuard guard(dense.device());
   const int64_t M = dense.size(0), K = dense.size(1);
   auto iopt = torch::dtype(torch::kInt32).device(dense.device());
   auto crow = torch::empty({M + 1}, iopt);
   int64_t nnz = 0;
+  if (M * K > 0 && M * K <= g_onepass_max_elems) {
+    // one pass over the dense matrix into worst-case sized arrays (the caching allocator hands them out without a
+    // cudaMalloc after the first call); the results are views of the first nnz entries
+    auto col = torch::empty({M * K}, iopt);
+    auto val = torch::empty({M * K}, dense.options());
+    const size_t sb = b200_dense_to_csr_onepass_scratch_bytes(M, K);
+    auto scratch = torch::empty({(int64_t)sb}, torch::dtype(torch::kUInt8).device(dense.device()));
+    check(b200_dense_to_csr_onepass(dense.data_ptr<float>(), M, K, ld_of(dense), crow.data_ptr<int>(),
+                                    col.data_ptr<int>(), val.data_ptr<float>(), M * K, scratch.data_ptr(), sb, &nnz,
+                                    cur_stream()));
+    if (compact) return {crow, col.narrow(0, 0, nnz).clone(), val.narrow(0, 0, nnz).clone()};
+    return {crow, col.narrow(0, 0, nnz), val.narrow(0, 0, nnz)};
+  }
   check(b200_dense_to_csr_count(dense.data_ptr<float>(), M, K, ld_of(dense), crow.data_ptr<int>(), &nnz,
                                 cur_stream()));
   auto col = torch::empty({nnz}, iopt);
@@ -310,7 +328,7 @@ std::vector<torch::Tensor> dense_to_csr(torch::Tensor dense) {
 
 // A stack of L dense [M,K] matrices ([L*M, K] view) -> block-diagonal CSR [L*M, L*K] on the device.
 std::vector<torch::Tensor> dense_to_csr_block_diag(torch::Tensor dense2d, int64_t M) {
-  auto out = dense_to_csr(dense2d);
+  auto out = dense_to_csr(dense2d, false);
   const int64_t rows = dense2d.size(0), K = dense2d.size(1);
   c10::cuda::CUDAGuard guard(dense2d.device());
   check(b200_csr_block_diag_cols(out[0].data_ptr<int>(), out[1].data_ptr<int>(), rows, M, K, cur_stream()));
@@ -466,7 +484,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("cusparse_clean", &cusparse_clean, "Cleanup function for CuSPARSE");
 
   // engine extras
-  m.def("dense_to_csr", &dense_to_csr, "dense [M,K] -> (crow int32, col int32, val) on the device");
+  m.def("dense_to_csr", &dense_to_csr, "dense [M,K] -> (crow int32, col int32, val) on the device",
+        py::arg("dense"), py::arg("compact") = false);
+  m.def("set_onepass_max_elems", [](int64_t n) { g_onepass_max_elems = n; });
   m.def("dense_to_csr_block_diag", &dense_to_csr_block_diag,
         "stack of L dense [M,K] matrices given as [L*M,K] -> block-diagonal CSR (crow, col, val) of [L*M, L*K]");
   m.def("csr_transpose", &csr_transpose, "CSR(A) -> (crow, col, val, perm) of A^T");

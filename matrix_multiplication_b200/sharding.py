@@ -9,6 +9,13 @@ into contiguous row ranges of equal *cost* and no reduction ever crosses ranks).
   shard_csr      the local CSR of one shard (row_ptr rebased to 0)
   RowGather      every rank ends up with all row blocks of C: one symmetric [M,N] buffer per rank,
                  the local SpMM writes its block in place, the other blocks arrive over NCCL
+                 (all_gather: one grouped collective; gather_to: only one rank collects)
+  backward       grad_A is local to a shard (SDDMM on the shard's pattern with the shard's rows of grad_C);
+                 grad_B = sum_g A_g^T grad_C_g: every rank forms its [K, N] partial product over its cached
+                 transposed shard and the partials are reduce-scattered (rank g ends with rows
+                 [g K / G, (g + 1) K / G) of grad_B), matmuls.py:250,253 being the formulas.  Sharding A^T by rows
+                 and all-gathering grad_C instead moves the same (G - 1) / G * 4 K N bytes per rank for square
+                 operands and needs a second, differently balanced sharding of A: not built.
 '''
 from __future__ import annotations
 
@@ -54,6 +61,11 @@ class RowGather:
         return self.blocks[self.rank]
 
     def all_gather(self):
+        '''Every rank receives every other rank's row block.  NCCL: ONE grouped collective (all_gather with unequal
+        block sizes is issued by torch as a single ncclGroup of broadcasts); other backends: one broadcast per owner.'''
+        if self.dist.get_backend() == 'nccl' and all(b.numel() > 0 for b in self.blocks):
+            self.dist.all_gather(list(self.blocks), self.local)
+            return self.buffer
         works = []
         for g in range(self.world):
             if self.blocks[g].numel() == 0:
@@ -62,6 +74,36 @@ class RowGather:
         for wk in works:
             wk.wait()
         return self.buffer
+
+    def gather_to(self, dst: int = 0):
+        '''Only rank ``dst`` collects all row blocks (north_star: "C gathered via NCCL"): one batch of point-to-point
+        transfers; dst's NVLink ingress is the bound ((world - 1) / world of C).'''
+        ops = []
+        if self.rank == dst:
+            for g in range(self.world):
+                if g != dst and self.blocks[g].numel() > 0:
+                    ops.append(self.dist.P2POp(self.dist.irecv, self.blocks[g], g))
+        elif self.local.numel() > 0:
+            ops.append(self.dist.P2POp(self.dist.isend, self.local, dst))
+        if ops:
+            for wk in self.dist.batch_isend_irecv(ops):
+                wk.wait()
+        return self.buffer
+
+
+def reduce_scatter_rows(partial, out, dist):
+    '''out[K / world, N] = rows [rank K / world, (rank + 1) K / world) of the sum over ranks of partial[K, N]
+    (the grad_B exchange of the row-sharded backward).  K must divide by the world size.'''
+    world, rank = dist.get_world_size(), dist.get_rank()
+    K = partial.shape[0]
+    assert K % world == 0 and out.shape[0] == K // world
+    if dist.get_backend() == 'nccl':
+        dist.reduce_scatter_tensor(out, partial)
+    else:  # gloo (CPU tests): all-reduce, keep the own slice
+        tmp = partial.clone()
+        dist.all_reduce(tmp)
+        out.copy_(tmp[rank * (K // world):(rank + 1) * (K // world)])
+    return out
 
 
 class SymmetricRowGather:

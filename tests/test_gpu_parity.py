@@ -153,6 +153,42 @@ def test_dense_to_csr_random(shape):
     np.testing.assert_array_equal(bits(va), bits(ova))
 
 
+@pytest.mark.parametrize("shape,dens", [((1, 64), 0.5), ((3, 129), 0.3), ((40, 512), 0.1), ((37, 513), 0.1),
+                                        ((300, 2000), 0.02), ((513, 1023), 0.3), ((64, 4096), 0.9), ((5000, 65), 0.2),
+                                        ((2048, 3000), 0.001), ((100, 70000), 0.05)])
+def test_dense_to_csr_one_pass(shape, dens):
+    """b200_dense_to_csr_onepass (count + decoupled look-back + fill in one kernel): bit-exact against the oracle on
+    ragged widths, rows spanning several chunks / tiles, empty and full rows, special values."""
+    import torch
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    d = (rng.standard_normal(shape) * (rng.random(shape) < dens)).astype(np.float32)
+    d.flat[:: 17] = -0.0
+    d.flat[5 % d.size] = np.nan
+    d.flat[3 % d.size] = np.float32(1e-42)  # denormal: kept
+    if shape[0] > 2:
+        d[1] = 0      # an empty row
+        d[2] = 1.5    # a full row
+    orp, oci, ova = oracle.dense_to_csr(d)
+    dd = torch.from_numpy(d).to("cuda:0")
+    crow, col, val, nnz = capi.dense_to_csr_onepass_device(dd)
+    assert nnz == len(oci)
+    np.testing.assert_array_equal(crow.cpu().numpy(), orp)
+    np.testing.assert_array_equal(col[:nnz].cpu().numpy(), oci)
+    np.testing.assert_array_equal(bits(val[:nnz].cpu().numpy()), bits(ova))
+    # a strided window (leading dimension > K)
+    if shape[1] % 4 == 0 and shape[1] >= 64:
+        big = torch.zeros(shape[0], shape[1] + 8, device="cuda:0")
+        big[:, :shape[1]] = dd
+        crow2, col2, val2, nnz2 = capi.dense_to_csr_onepass_device(big[:, :shape[1]])
+        assert nnz2 == nnz and torch.equal(crow2, crow) and torch.equal(col2[:nnz], col[:nnz])
+    # too little room: reported, row_ptr complete, the second phase finishes the job
+    if nnz > 8:
+        with pytest.raises(capi.B200Error) as e:
+            capi.dense_to_csr_onepass_device(dd, capacity=nnz // 2)
+        assert e.value.status == capi.ERR_INVALID and e.value.nnz == nnz
+        np.testing.assert_array_equal(e.value.crow.cpu().numpy(), orp)
+
+
 # ---- transpose (bit-exact) and backward ----------------------------------------------------------------
 @pytest.mark.parametrize("case", [(1, 1, 1.0), (50, 70, 0.2), (700, 300, 0.05), (300, 5000, 0.01), (2000, 3, 0.5)])
 def test_transpose_bit_exact(case):

@@ -41,7 +41,24 @@ def _worker(rank, world, port, out_dir):
     gather.local.copy_(torch.from_numpy(local))
     full = gather.all_gather().numpy()
     ref = oracle.spmm_f64(rp, ci, va, shape, B)
-    np.save(Path(out_dir) / f"err_{rank}.npy", np.array([oracle.rel_err(full, ref), r0, r1]))
+    # gather-to-one-rank: rank 0 alone collects
+    g0 = sharding.RowGather(bounds, N, torch.device("cpu"), dist)
+    g0.buffer.zero_()
+    g0.local.copy_(torch.from_numpy(local))
+    only0 = g0.gather_to(0).numpy()
+    err_g0 = oracle.rel_err(only0, ref) if rank == 0 else 0.0
+    # sharded backward: grad_A is local, grad_B = sum over ranks of A_g^T G_g, reduce-scattered by rows
+    G = synthetic.dense_operand(shape[0], N, seed=5)
+    part = oracle.spmm_t_f64(l_rp, l_ci, l_va, (r1 - r0, shape[1]), G[r0:r1]).astype(np.float32)
+    K = shape[1]
+    mine = torch.empty(K // world, N)
+    sharding.reduce_scatter_rows(torch.from_numpy(part), mine, dist)
+    ref_gb = oracle.spmm_t_f64(rp, ci, va, shape, G)[rank * (K // world):(rank + 1) * (K // world)]
+    err_gb = oracle.rel_err(mine.numpy(), ref_gb)
+    ga = oracle.sddmm_f64(l_rp, l_ci, (r1 - r0, K), G[r0:r1], B)
+    p0, p1 = int(rp[r0]), int(rp[r1])
+    err_ga = oracle.rel_err(ga, oracle.sddmm_f64(rp, ci, shape, G, B)[p0:p1])
+    np.save(Path(out_dir) / f"err_{rank}.npy", np.array([oracle.rel_err(full, ref), r0, r1, err_g0, err_gb, err_ga]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,6 +70,9 @@ def test_two_rank_row_shards_tile_the_product(tmp_path):
     e0, e1 = np.load(tmp_path / "err_0.npy"), np.load(tmp_path / "err_1.npy")
     assert e0[0] <= 1e-6 and e1[0] <= 1e-6
     assert e0[1] == 0 and e0[2] == e1[1] and e1[2] == 1024
+    assert e0[3] <= 1e-6, "gather_to(0) must leave all of C on rank 0"
+    assert max(e0[4], e1[4]) <= 1e-6, "reduce-scattered grad_B differs from A^T G"
+    assert max(e0[5], e1[5]) <= 1e-12, "shard-local grad_A differs from the full SDDMM"
 
 
 def test_cost_balanced_bounds_beat_pure_nnz_balance_on_rows():
