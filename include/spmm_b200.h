@@ -72,7 +72,8 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  * pipeline      : forward kernel variant, 0 = shipped (profiles/r1_variant_sweep.md lists the alternatives).
  * flat_min_n    : smallest N served by the one-lane-group kernel (default 24; below it lane groups share a warp).
  * tc_mode       : block-dense tensor-core path: 0 never, 1 auto (default), 2 whenever the shape allows it.
- * tc_min_density_pct : auto rule threshold, nnz / (M*K) in percent (default 4).
+ * tc_min_density_pct : auto rule floor, nnz / (M*K) in percent (default 2); above it a measured cost model of the two
+ *                 paths decides (small or very sparse problems stay on the gather kernels).
  * tc_kind       : split-precision element kind: 0 = tf32 hi + lo, 1 = fp16 hi + lo with per-row / per-column scaling.
  * tc_nt, tc_terms, tc_chunk : tile width override (multiple of 64), which split-precision products are issued (bit mask,
  *                 7 = all), k-tiles accumulated in TMEM between two fp32 register accumulations (accuracy studies). */
@@ -199,8 +200,8 @@ int b200_plan_forward_peers(b200_plan* plan, const float* d_B, int64_t ldb, int6
  *   B200_OP_RELU         : max(x, 0) applied in the epilogue;
  *   d_bias               : optional [M] vector added to every column of C (NULL = none);
  *   B200_OP_NO_TC / B200_OP_FORCE_TC : override the path choice below.
- * Path choice (also applied by b200_plan_forward / b200_plan_backward_B): when the operand is dense enough
- * (option tc_min_density_pct, default 4 % of M*K) and N >= 32, the plan densifies the non-empty 128 x 32 tiles of
+ * Path choice (also applied by b200_plan_forward / b200_plan_backward_B): when a measured cost model says the
+ * tiles win (large enough problem, density above ~4-5 %, N >= 8), the plan densifies the non-empty 128 x 32 tiles of
  * A once (fp32 split into tf32 hi + lo) and the product runs on the tensor cores (tcgen05.mma kind::tf32, three
  * products per k-step, fp32 accumulation in TMEM): fp32-grade accuracy (rel-err <= 1e-5 vs fp64 is tested), 2-6x the
  * gather kernels' throughput.  This replaces the reference's cuSPARSE call for dense-ish operands
@@ -217,7 +218,14 @@ int b200_plan_forward_ex(b200_plan* plan, const float* d_B, int64_t ldb, int64_t
 /* grad_B = A^T * G with the same operand options (d_G may be G^T [N, M], d_dB may be written as dB^T [N, K]). */
 int b200_plan_backward_B_ex(b200_plan* plan, const float* d_G, int64_t ldg, int64_t N, float* d_dB, int64_t lddb,
                             uint32_t flags, void* stream);
-/* 1 if a product with N dense columns over this side of the plan (0 = A, 1 = A^T) would take the tensor-core tiles
+/* grad of the CSR values with the same path choice: on dense-enough operands D = G * B^T runs on the tensor-core tiles
+ * (both operands packed per call, contraction over the N dense columns) and the epilogue writes only the entries on
+ * A's pattern.  B200_OP_B_TRANSPOSED: BOTH operands are given transposed, d_G as [N, M] and d_B as [N, K] (the
+ * gradient and the activations of an FC layer as they are; tensor-core path only). */
+int b200_plan_backward_A_ex(b200_plan* plan, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb, int64_t N,
+                            float* d_dval, uint32_t flags, void* stream);
+/* 1 if a product with N dense columns over this side of the plan (0 = A: forward, 1 = A^T: backward_B, 2 = the SDDMM
+ * of backward_A) would take the tensor-core tiles
  * under the current options and flags, else 0.  Callers that hold their operands transposed use it to decide whether
  * to pass them as they are (B200_OP_*_TRANSPOSED are served efficiently by the tiles only). */
 int b200_plan_would_use_tc(const b200_plan* plan, int side, int64_t N, uint32_t flags);

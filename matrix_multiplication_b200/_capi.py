@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_plan_forward_peers": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp), C.c_int, _vp, _vp]),
     "b200_plan_forward_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, C.c_uint32, _vp]),
     "b200_plan_backward_B_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, C.c_uint32, _vp]),
+    "b200_plan_backward_A_ex": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, C.c_uint32, _vp]),
     "b200_plan_would_use_tc": (C.c_int, [_vp, C.c_int, _i64, C.c_uint32]),
     "b200_plan_tc_info": (C.c_int, [_vp, C.c_int, _i64p, _i64p, C.POINTER(C.c_int)]),
     "b200_tc_last_timeout": (C.c_int, [_vp, C.POINTER(C.c_int)]),
@@ -350,6 +351,13 @@ class Plan:
     def backward_A(self, G, B, dval, stream=0):
         N = G.shape[1]
         check(lib().b200_plan_backward_A(self._h, _dp(G), N, _dp(B), N, N, _dp(dval), C.c_void_p(stream)))
+        return dval
+
+    def backward_A_ex(self, G, B, dval, flags=0, stream=0):
+        """grad of the CSR values; with OP_B_TRANSPOSED, G is [N, M] and B is [N, K]."""
+        N = G.shape[0] if flags & OP_B_TRANSPOSED else G.shape[1]
+        check(lib().b200_plan_backward_A_ex(self._h, _dp(G), G.stride(0), _dp(B), B.stride(0), N, _dp(dval), flags,
+                                            C.c_void_p(stream)))
         return dval
 
     def values_updated(self):

@@ -119,6 +119,10 @@ struct b200_plan {
   void* tc_ws = nullptr;               // [non-finite flag | debug word | packed dense operand]
   size_t tc_ws_bytes = 0;
   int last_path = 0;                   // 0 gather kernels, 1 tensor-core tiles, 2 strided fallback
+  TcSample samp;                       // A's pattern as bit masks, for the tensor-core SDDMM's sampling epilogue
+  bool samp_built = false, samp_failed = false;
+  void* sd_ws = nullptr;               // packed G and B of the tensor-core SDDMM
+  size_t sd_ws_bytes = 0;
 };
 
 // Boundaries depend on (row_ptr, W, heavy) only: compute once per plan side, reuse for every N.
@@ -507,7 +511,8 @@ int b200_plan_destroy(b200_plan* p) {
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
   cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd); cudaFree(p->d_peers);
   cudaFree(p->cnt[0]); cudaFree(p->cnt[1]);
-  cudaFree(p->hB); cudaFree(p->hC); cudaFree(p->tc_ws);
+  cudaFree(p->hB); cudaFree(p->hC); cudaFree(p->tc_ws); cudaFree(p->sd_ws);
+  tc_sample_free(&p->samp);
   tc_store_free(&p->tc[0]); tc_store_free(&p->tc[1]);
   for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
   for (int j = 0; j < 2; ++j) for (int i = 0; i < 16; ++i) if (p->hev[j][i]) cudaEventDestroy(p->hev[j][i]);
@@ -582,7 +587,13 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
 }
 
 // Should this product run on the block-dense tensor-core path?  ("crossover rule")
-static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t flags) {
+// Auto mode compares two measured cost models (B200, profiles/r2_tc_crossover.md):
+//   gather kernels : 12 us + nnz * N / 5.0e6 us   (one gathered B element per FMA; ~2e6 per us below 24 columns)
+//   tensor tiles   : 28 us + max(streaming the densified tiles, the MMAs):
+//                      tile bytes (x column blocks when they exceed L2) / 5.5e6 B per us,
+//                      6 * M_pad * K * N_pad / R, R = 1.3e9 (fp16 split) or 0.65e9 (tf32 split) flop per us
+// so small problems stay on the gather kernels (launch-bound: config 1-2), and large ones switch at ~4-5 % density.
+static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t flags, bool sddmm = false) {
   if (flags & B200_OP_NO_TC) return false;
   const int mode = options().tc_mode;
   if (mode == 0 && !(flags & B200_OP_FORCE_TC)) return false;
@@ -592,10 +603,25 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
   if (MB * KT > ((int64_t)1 << 26)) return false;
   if (std::min<int64_t>(MB * KT, p->nnz) * 32768 > ((int64_t)24 << 30)) return false;  // densified tiles
   if ((flags & B200_OP_FORCE_TC) || mode == 2) return true;
-  // auto: a dense-enough operand (every gathered B element feeds one FMA on the gather path, 128 on this one)
-  // and enough dense columns to fill a tile
   const double density = (double)p->nnz / ((double)M * (double)K);
-  return N >= 32 && density * 100.0 >= (double)options().tc_min_density_pct;
+  if (density * 100.0 < (double)options().tc_min_density_pct) return false;
+  const double n_pad = (double)((N + 63) / 64 * 64);
+  const double t_gather = 12.0 + (double)p->nnz * (double)N / (N < 24 ? 2.0e6 : 5.0e6);
+  const bool f16 = options().tc_kind == 1;
+  const double tile_bytes = (double)(MB * 128) * (double)K * (f16 ? 4.0 : 8.0);
+  const double passes = tile_bytes > 64e6 ? (double)((N + 255) / 256) : 1.0;
+  const double t_stream = tile_bytes * passes / 5.5e6;
+  const double t_mma = 6.0 * (double)(MB * 128) * (double)K * n_pad / (f16 ? 1.3e9 : 0.65e9);
+  if (sddmm) {
+    // grad of the values: every output tile of the M x K product is computed and sampled, so the tile count (not the
+    // contraction length N) dominates: 30 us + M_pad * K / 4.5e5 + MMAs; the gather SDDMM runs at ~3.3e6 nnz*N per us
+    // (1.25e6 below 24 columns)
+    const double t_g = 12.0 + (double)p->nnz * (double)N / (N < 24 ? 1.25e6 : 3.3e6);
+    const double t_t = 30.0 + (double)(MB * 128) * (double)K / 4.5e5 + t_mma;
+    return t_t < t_g;
+  }
+  const double t_tc = 28.0 + std::max(t_stream, t_mma);
+  return t_tc < t_gather;
 }
 
 static int plan_ensure_tc(b200_plan* p, int side, const int* row_ptr, const int* col, const float* val, int M,
@@ -692,7 +718,9 @@ int b200_plan_backward_B_ex(b200_plan* p, const float* d_G, int64_t ldg, int64_t
 }
 
 int b200_plan_would_use_tc(const b200_plan* p, int side, int64_t N, uint32_t flags) {
-  if (p == nullptr || (side != 0 && side != 1) || p->tc_failed[side]) return 0;
+  if (p == nullptr || side < 0 || side > 2) return 0;
+  if (side == 2) return (!p->samp_failed && plan_wants_tc(p, p->M, p->K, N, flags, true)) ? 1 : 0;
+  if (p->tc_failed[side]) return 0;
   return plan_wants_tc(p, side == 0 ? p->M : p->K, side == 0 ? p->K : p->M, N, flags) ? 1 : 0;
 }
 
@@ -783,22 +811,65 @@ int b200_plan_backward_B(b200_plan* p, const float* d_G, int64_t ldg, int64_t N,
                       nullptr, 0u, (cudaStream_t)stream);
 }
 
-int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,
-                         int64_t N, float* d_dval, void* stream) {
-  B200_REQUIRE(p != nullptr, "null plan");
+static int plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb, int64_t N,
+                           float* d_dval, uint32_t flags, cudaStream_t s) {
+  const bool tr = (flags & B200_OP_B_TRANSPOSED) != 0;  // G given as [N, M], B as [N, K]
   B200_REQUIRE(N >= 0 && N < 0x7fffffffLL, "N out of range");
-  B200_REQUIRE(ldg >= N && ldb >= N && ldg < 0x7fffffffLL && ldb < 0x7fffffffLL, "bad leading dimension");
+  B200_REQUIRE(ldg >= (tr ? p->M : N) && ldb >= (tr ? p->K : N) && ldg < 0x7fffffffLL && ldb < 0x7fffffffLL,
+               "bad leading dimension");
   if (p->nnz == 0 || p->M == 0) return B200_OK;
   B200_REQUIRE(d_dval != nullptr && (N == 0 || (d_G && d_B)), "null G / B / output");
-  cudaStream_t s = (cudaStream_t)stream;
   int rc_dev = plan_check_device(p);
   if (rc_dev) return rc_dev;
+  if (N > 0 && !p->samp_failed && plan_wants_tc(p, p->M, p->K, N, flags, /*sddmm=*/true)) {
+    // D = G * B^T on the tensor cores, sampled on A's pattern
+    int rc = B200_OK;
+    if (!p->samp_built) {
+      rc = tc_sample_build(p->row_ptr, p->col, p->M, p->K, p->nnz, &p->samp, s);
+      if (rc == B200_OK) p->samp_built = true;
+      else p->samp_failed = true;
+    }
+    if (rc == B200_OK) {
+      const int kind = options().tc_kind;
+      const int nt = options().tc_nt > 0 ? options().tc_nt : tc_pick_nt((p->M + 127) / 128, p->K, device_sm_count());
+      const size_t need = tc_sddmm_ws_bytes(p->M, p->K, (int)N, nt, kind);
+      if (p->sd_ws_bytes < need) {
+        if (p->sd_ws) { B200_CUDA_OK(cudaStreamSynchronize(s)); B200_CUDA_OK(cudaFree(p->sd_ws)); p->sd_ws = nullptr; p->sd_ws_bytes = 0; }
+        if (cudaMalloc(&p->sd_ws, need) != cudaSuccess) {
+          cudaGetLastError();
+          set_error("cudaMalloc of %zu bytes for the packed SDDMM operands failed", need);
+          return B200_ERR_ALLOC;
+        }
+        p->sd_ws_bytes = need;
+        B200_CUDA_OK(cudaMemsetAsync(p->sd_ws, 0, 256, s));
+      }
+      p->last_path = 1;
+      return launch_tc_sddmm(p->samp, p->row_ptr, p->col, d_G, ldg, d_B, ldb, (int)N, tr, d_dval, p->sd_ws,
+                             p->sd_ws_bytes, nt, kind, s);
+    }
+    if (flags & B200_OP_FORCE_TC) return rc;
+  }
+  B200_REQUIRE(!tr, "transposed SDDMM operands need the tensor-core path (b200_plan_would_use_tc)");
   if (p->sd_bnd == nullptr) {
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->sd_bnd), sddmm_bounds_bytes(p->M, p->nnz)));
     int rc = launch_sddmm_partition(p->row_ptr, p->M, p->nnz, p->sd_bnd, s);
     if (rc) return rc;
   }
+  p->last_path = 0;
   return launch_sddmm(p->row_ptr, p->col, p->M, p->nnz, d_G, ldg, d_B, ldb, (int)N, d_dval, p->sd_bnd, s);
+}
+
+int b200_plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,
+                         int64_t N, float* d_dval, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  return plan_backward_A(p, d_G, ldg, d_B, ldb, N, d_dval, 0u, (cudaStream_t)stream);
+}
+
+int b200_plan_backward_A_ex(b200_plan* p, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb,
+                            int64_t N, float* d_dval, uint32_t flags, void* stream) {
+  B200_REQUIRE(p != nullptr, "null plan");
+  B200_REQUIRE((flags & (B200_OP_RELU | B200_OP_C_TRANSPOSED)) == 0, "flags that do not apply to the SDDMM");
+  return plan_backward_A(p, d_G, ldg, d_B, ldb, N, d_dval, flags, (cudaStream_t)stream);
 }
 
 // ---- host-buffer entry points ------------------------------------------------------------

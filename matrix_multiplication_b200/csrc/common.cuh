@@ -59,7 +59,7 @@ struct Options {
   int tc_terms = 7;        // which split-precision products are issued: 1 hi*hi, 2 hi*lo, 4 lo*hi
   int tc_chunk = 4;        // k-tiles accumulated in TMEM between two fp32 register accumulations
   int tc_kind = 1;         // 0 = tf32 hi/lo split, 1 = fp16 hi/lo split with row / column scaling (default)
-  int tc_min_density_pct = 4;  // auto rule: nnz / (M*K) at or above this percentage
+  int tc_min_density_pct = 2;  // auto rule: never below this density (percent of M*K); above it a cost model decides
 };
 Options& options();
 
@@ -314,6 +314,18 @@ size_t tc_pack_b_bytes(int K, int N, int nt, int kind);
 int launch_tc_forward(const TcStore& st, const int* row_ptr, const int* col, const float* val, const float* B,
                       long long ldb, int N, float* C, long long ldc, const float* bias, unsigned flags, void* ws,
                       size_t ws_bytes, int nt, cudaStream_t s);
+// pattern of a CSR matrix for the tensor-core SDDMM's sampling epilogue
+struct TcSample {
+  int M = 0, K = 0, groups = 0;
+  uint32_t* mask = nullptr;  // [groups][M] bit j of (g, m): (m, 32 g + j) is a non-zero
+  int* off = nullptr;        // [groups][M] position (in the CSR value array) of the group's first non-zero
+};
+int tc_sample_build(const int* row_ptr, const int* col, int M, int K, int nnz, TcSample* sm, cudaStream_t s);
+void tc_sample_free(TcSample* sm);
+size_t tc_sddmm_ws_bytes(int M, int K, int N, int nt, int kind);
+int launch_tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, const float* G, long long ldg,
+                    const float* B, long long ldb, int N, bool transposed, float* out, void* ws, size_t ws_bytes,
+                    int nt, int kind, cudaStream_t s);
 // generic strided CSR SpMM (any B / C strides, bias, ReLU): the correctness fallback of the extended forward
 int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, int M, int N, const float* B,
                         long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,

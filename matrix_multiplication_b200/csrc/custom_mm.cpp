@@ -434,15 +434,18 @@ struct PlanHandle {
                                   (uint32_t)flags, cur_stream()));
     return dB;
   }
-  // grad of the CSR values on A's pattern
-  torch::Tensor backward_A(const torch::Tensor& G, const torch::Tensor& B) {
+  // grad of the CSR values on A's pattern; with B200_OP_B_TRANSPOSED both operands are [N, .] (tensor-core path)
+  torch::Tensor backward_A(const torch::Tensor& G, const torch::Tensor& B, int64_t flags) {
     check_dense(G, "G");
     check_dense(B, "B");
-    TORCH_CHECK(G.size(0) == M && B.size(0) == K && G.size(1) == B.size(1), "G must be [M,N] and B [K,N]");
+    const bool tr = flags & B200_OP_B_TRANSPOSED;
+    const int64_t N = tr ? G.size(0) : G.size(1);
+    TORCH_CHECK((tr ? G.size(1) : G.size(0)) == M && (tr ? B.size(1) : B.size(0)) == K &&
+                (tr ? B.size(0) : B.size(1)) == N, "G must be [M,N] and B [K,N] (or [N,M] and [N,K] when transposed)");
     c10::cuda::CUDAGuard guard(G.device());
     auto out = torch::empty({nnz}, G.options());
-    check(b200_plan_backward_A(plan, G.data_ptr<float>(), ld_of(G), B.data_ptr<float>(), ld_of(B), G.size(1),
-                               out.data_ptr<float>(), cur_stream()));
+    check(b200_plan_backward_A_ex(plan, G.data_ptr<float>(), ld_of(G), B.data_ptr<float>(), ld_of(B), N,
+                                  out.data_ptr<float>(), (uint32_t)flags, cur_stream()));
     return out;
   }
   void values_updated() { check(b200_plan_values_updated(plan)); }
@@ -502,7 +505,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("forward", &PlanHandle::forward, py::arg("B"), py::arg("C"), py::arg("bias") = py::none(),
            py::arg("flags") = 0)
       .def("backward_B", &PlanHandle::backward_B, py::arg("G"), py::arg("dB"), py::arg("flags") = 0)
-      .def("backward_A", &PlanHandle::backward_A, py::arg("G"), py::arg("B"))
+      .def("backward_A", &PlanHandle::backward_A, py::arg("G"), py::arg("B"), py::arg("flags") = 0)
       .def("values_updated", &PlanHandle::values_updated)
       .def("would_use_tc", &PlanHandle::would_use_tc, py::arg("N"), py::arg("side") = 0, py::arg("flags") = 0)
       .def("last_path", &PlanHandle::last_path);

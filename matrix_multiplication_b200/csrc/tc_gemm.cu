@@ -467,6 +467,16 @@ struct TcParams {
   const float* val;
   const float* B;
   long long b_sk, b_sn;
+  // SDDMM mode (grad of the CSR values): A operand = packed G (a_tiles, NGa groups of 8 rows per k-tile), B operand
+  // = packed B, contraction over the KT k-tiles of the dense column index; the epilogue samples the tile at A's
+  // non-zeros: per (32-column group, row) a bit mask of the pattern and the position of the group's first non-zero
+  int NGa, KT;
+  const uint32_t* amax;       // fp16 kind: row maxima of G (uint bits)
+  const uint32_t* samp_mask;  // [groups][M]
+  const int* samp_off;        // [groups][M]
+  int groups;
+  const float* G;             // raw G for the CSR-order pass
+  long long g_sm, g_sn;
 };
 
 // exit protocol: the last CTA to leave re-arms the non-finite flag and the ticket for the next launch
@@ -503,17 +513,45 @@ __device__ __forceinline__ void csr_order_spmm(const int* __restrict__ row_ptr, 
   }
 }
 
+// out[p] = sum_n G[row(p), n] * B[col(p), n] in CSR order with any strides: warp per row, lanes over n
+__device__ __forceinline__ void csr_order_sddmm(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int N,
+                                                const float* __restrict__ G, long long g_sm, long long g_sn,
+                                                const float* __restrict__ B, long long b_sk, long long b_sn,
+                                                float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < M;
+       row += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
+    for (int p = rs; p < re; ++p) {
+      const long long c = __ldg(col + p);
+      float acc = 0.f;
+      for (int n = lane; n < N; n += 32)
+        acc = fmaf(__ldg(G + row * g_sm + (long long)n * g_sn), __ldg(B + c * b_sk + (long long)n * b_sn), acc);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) out[p] = acc;
+    }
+  }
+}
+
 // The tensor core adds into its TMEM accumulator with truncation (measured: a K = 16384 contraction of positive
 // values comes out 1.3e-4 low), so an accumulator only ever holds `chunk` k-tiles (<= 48 additions, bias <= 1.5e-6
 // of the partial sum); the epilogue warps add the partial sums in fp32 registers with round-to-nearest.  The two
 // TMEM buffers alternate per chunk: MMAs of chunk i+1 overlap the drain of chunk i.
-template <int KIND>
+//
+// SDDMM = true: the same pipeline computes D = G * B^T tile by tile (contraction over the dense column index) and the
+// epilogue writes only the entries on A's pattern: grad of the CSR values (matmuls.py:250 restricted to the pattern).
+template <int KIND, bool SDDMM>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p) {
   extern __shared__ unsigned char tc_smem_raw[];
-  if (*reinterpret_cast<const volatile int*>(p.ctl) != 0) {  // Inf / NaN in the dense operand (uniform over the grid)
-    const bool ctr = (p.flags & 2u) != 0;
-    csr_order_spmm(p.row_ptr, p.col, p.val, p.M, p.N, p.B, p.b_sk, p.b_sn, p.C, ctr ? 1 : p.ldc, ctr ? p.ldc : 1, p.bias,
-                   (p.flags & 4u) != 0);
+  if (*reinterpret_cast<const volatile int*>(p.ctl) != 0) {  // Inf / NaN in a dense operand (uniform over the grid)
+    if constexpr (SDDMM) {
+      csr_order_sddmm(p.row_ptr, p.col, p.M, p.N, p.G, p.g_sm, p.g_sn, p.B, p.b_sk, p.b_sn, p.C);
+    } else {
+      const bool ctr = (p.flags & 2u) != 0;
+      csr_order_spmm(p.row_ptr, p.col, p.val, p.M, p.N, p.B, p.b_sk, p.b_sn, p.C, ctr ? 1 : p.ldc, ctr ? p.ldc : 1,
+                     p.bias, (p.flags & 4u) != 0);
+    }
     tc_exit_ticket(p.ctl);
     return;
   }
@@ -555,14 +593,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       bool ok = true;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int mb = tile / p.NB, nb = tile % p.NB;
-        const int t0 = __ldg(p.blk_ptr + mb), t1 = __ldg(p.blk_ptr + mb + 1);
+        const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
         for (int t = t0; t < t1; ++t) {
           ok = mbar_wait_bounded(empty + stage, phase ^ 1u, p.ctl + 1, 100 + stage);
           if (!ok) break;
-          const int kt = __ldg(p.blk_kt + t);
+          const int kt = SDDMM ? t : __ldg(p.blk_kt + t);
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(full + stage, (uint32_t)stage_bytes);
-          tma_bulk_g2s(sa, p.a_tiles + (size_t)t * A_TILE, A_TILE, full + stage);
+          const unsigned char* a_src = SDDMM ? p.a_tiles + ((size_t)kt * p.NGa + (size_t)mb * (BM / 8)) * ATOM
+                                             : p.a_tiles + (size_t)t * A_TILE;
+          tma_bulk_g2s(sa, a_src, A_TILE, full + stage);
           tma_bulk_g2s(sa + A_TILE, p.b_pack + ((size_t)kt * p.NG + (size_t)nb * (p.Nt / 8)) * ATOM,
                        (uint32_t)p.Nt * 256u, full + stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -579,7 +619,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       bool ok = true;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int mb = tile / p.NB;
-        const int t0 = __ldg(p.blk_ptr + mb), t1 = __ldg(p.blk_ptr + mb + 1);
+        const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
         for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
           const int as = (int)(g & 1u);
           ok = mbar_wait_bounded(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as);
@@ -620,7 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
     bool ok = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       const int mb = tile / p.NB, nb = tile % p.NB;
-      const int t0 = __ldg(p.blk_ptr + mb), t1 = __ldg(p.blk_ptr + mb + 1);
+      const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -646,6 +686,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       }
       if (!ok) break;
       const int m = mb * BM + q * 32 + lane;
+      if constexpr (SDDMM) {
+        // sample the tile on A's pattern: bit j of the mask <=> (m, 32 g + j) is a non-zero; its position in the CSR
+        // value array is the group's offset plus the number of set bits below j
+        float rs = 1.f;
+        if constexpr (KIND == KIND_F16) rs = (m < p.M) ? scale_down(scale_exp(__ldg(p.amax + m))) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k0 = nb * p.Nt + half * ntw + c * 32;
+          const int grp = k0 >> 5;
+          if (c * 32 < ntw && grp < p.groups && m < p.M) {
+            const uint32_t mask = __ldg(p.samp_mask + (size_t)grp * p.M + m);
+            const int base = __ldg(p.samp_off + (size_t)grp * p.M + m);
+            if (mask != 0u) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if ((mask >> j) & 1u) {
+                  float x = acc[c * 32 + j];
+                  if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp(__ldg(p.colmax + k0 + j)));
+                  p.C[base + __popc(mask & ((1u << j) - 1u))] = x;
+                }
+              }
+            }
+          }
+        }
+        continue;
+      }
       const float bias = (p.bias != nullptr && m < p.M) ? __ldg(p.bias + m) : 0.f;
       float rs = 1.f;
       if constexpr (KIND == KIND_F16) rs = (m < p.M) ? __ldg(p.row_scale + m) : 0.f;
@@ -823,63 +889,81 @@ size_t tc_pack_b_bytes(int K, int N, int nt, int kind) {
   return 256 + tc_colmax_bytes((int)NG * 8) + KT * NG * ATOM;
 }
 
+// Pack one dense operand for the tiles: `rows` rows (the operand's non-contracted index, padded to NG groups of 8)
+// by `depth` contraction values.  by_depth = true: memory is [depth][rows] (each contraction index is a row of
+// memory, e.g. B [K, N] for the forward); false: memory is [rows][depth] (e.g. B^T, or G [M, N] for the SDDMM).
+// fp16 kind: row maxima -> rmax (then the scaling), wide operands in one fused launch.
+template <int KIND>
+static int tc_pack_operand(const float* X, long long ld, int rows, int depth, bool by_depth, int KT, int NG,
+                           unsigned char* pack, uint32_t* rmax, int* ctl, cudaStream_t s) {
+  const int sms = device_sm_count();
+  const int total = KT * NG;
+  const int blocks = std::max(1, std::min((total + 7) / 8, sms * 8));
+  if (KIND == KIND_F16 && NG >= sms) {
+    if (!by_depth) tc_prepack_b_kernel<true><<<NG, 256, 0, s>>>(X, ld, depth, rows, KT, NG, pack, rmax, ctl);
+    else tc_prepack_b_kernel<false><<<NG, 256, 0, s>>>(X, ld, depth, rows, KT, NG, pack, rmax, ctl);
+    B200_LAUNCH_OK("tc_prepack_b_kernel");
+    return B200_OK;
+  }
+  if (KIND == KIND_F16) {
+    B200_CUDA_OK(cudaMemsetAsync(rmax, 0, tc_colmax_bytes(NG * 8), s));
+    if (!by_depth) {
+      tc_colmax_kernel<true><<<(unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, s>>>(X, ld, depth, rows, rmax, ctl);
+    } else {
+      dim3 grid((unsigned)((rows + 255) / 256),
+                (unsigned)std::max(1, std::min(depth, (sms * 8) / std::max(1, (rows + 255) / 256))));
+      tc_colmax_kernel<false><<<grid, 256, 0, s>>>(X, ld, depth, rows, rmax, ctl);
+    }
+    B200_LAUNCH_OK("tc_colmax_kernel");
+  }
+  if (!by_depth) tc_pack_b_kernel<KIND, true><<<blocks, 256, 0, s>>>(X, ld, depth, rows, KT, NG, pack, rmax, ctl);
+  else tc_pack_b_kernel<KIND, false><<<blocks, 256, 0, s>>>(X, ld, depth, rows, KT, NG, pack, rmax, ctl);
+  B200_LAUNCH_OK("tc_pack_b_kernel");
+  return B200_OK;
+}
+
+template <int KIND, bool SDDMM>
+static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
+  const int stage_bytes = A_TILE + p.Nt * 256;
+  p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes));
+  p.chunk = std::max(1, options().tc_chunk);
+  p.terms = options().tc_terms;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  B200_CUDA_OK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    B200_CUDA_OK(cudaFuncSetAttribute(tc_spmm_kernel<KIND, SDDMM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+    attr_set[dev & 63] = true;
+  }
+  const int grid = std::max(1, std::min(device_sm_count(), tiles));
+  tc_spmm_kernel<KIND, SDDMM><<<grid, TC_THREADS, smem, s>>>(p);
+  B200_LAUNCH_OK(SDDMM ? "tc_sddmm_kernel" : "tc_spmm_kernel");
+  return B200_OK;
+}
+
 template <int KIND>
 static int tc_launch(const TcStore& st, const int* row_ptr, const int* col, const float* val, const float* B,
                      long long ldb, int N, float* C, long long ldc, const float* bias, unsigned flags, void* ws, int nt,
                      cudaStream_t s) {
-  const int sms = device_sm_count();
   int* ctl = reinterpret_cast<int*>(ws);  // zero between launches (the kernel re-arms it on exit)
   const int NB = (N + nt - 1) / nt, NG = NB * (nt / 8);
   uint32_t* colmax = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ws) + 256);
   unsigned char* b_pack = reinterpret_cast<unsigned char*>(ws) + 256 + tc_colmax_bytes(NG * 8);
   const bool bt = (flags & 1u) != 0;
-  const int total = st.KT * NG;
-  const int blocks = std::min((total + 7) / 8, sms * 8);
-  if (KIND == KIND_F16 && NG >= sms) {  // wide operand: column maxima and packing in one launch
-    if (bt) tc_prepack_b_kernel<true><<<NG, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
-    else tc_prepack_b_kernel<false><<<NG, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
-    B200_LAUNCH_OK("tc_prepack_b_kernel");
-  } else {
-    if (KIND == KIND_F16) {
-      B200_CUDA_OK(cudaMemsetAsync(colmax, 0, tc_colmax_bytes(NG * 8), s));
-      if (bt) {
-        tc_colmax_kernel<true><<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(B, ldb, st.K, N, colmax, ctl);
-      } else {
-        dim3 grid((unsigned)((N + 255) / 256),
-                  (unsigned)std::max(1, std::min(st.K, (sms * 8) / std::max(1, (N + 255) / 256))));
-        tc_colmax_kernel<false><<<grid, 256, 0, s>>>(B, ldb, st.K, N, colmax, ctl);
-      }
-      B200_LAUNCH_OK("tc_colmax_kernel");
-    }
-    if (bt) tc_pack_b_kernel<KIND, true><<<blocks, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
-    else tc_pack_b_kernel<KIND, false><<<blocks, 256, 0, s>>>(B, ldb, st.K, N, st.KT, NG, b_pack, colmax, ctl);
-    B200_LAUNCH_OK("tc_pack_b_kernel");
-  }
+  int rc = tc_pack_operand<KIND>(B, ldb, N, st.K, /*by_depth=*/!bt, st.KT, NG, b_pack, colmax, ctl, s);
+  if (rc) return rc;
   TcParams p{};
   p.a_tiles = st.tiles; p.blk_ptr = st.blk_ptr; p.blk_kt = st.blk_kt;
   p.b_pack = b_pack; p.NG = NG;
   p.C = C; p.ldc = ldc; p.M = st.M; p.N = N; p.bias = bias; p.flags = flags;
   p.row_scale = st.row_scale; p.colmax = colmax;
   p.MB = st.MB; p.NB = NB; p.Nt = nt;
-  p.chunk = std::max(1, options().tc_chunk);
-  p.terms = options().tc_terms;
   p.ctl = ctl;
   p.row_ptr = row_ptr; p.col = col; p.val = val; p.B = B;
   p.b_sk = bt ? 1 : ldb; p.b_sn = bt ? ldb : 1;
-  const int stage_bytes = A_TILE + nt * 256;
-  p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  B200_CUDA_OK(cudaGetDevice(&dev));
-  if (!attr_set[dev & 63]) {
-    B200_CUDA_OK(cudaFuncSetAttribute(tc_spmm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[dev & 63] = true;
-  }
-  const int grid = std::min(sms, st.MB * NB);
-  tc_spmm_kernel<KIND><<<grid, TC_THREADS, smem, s>>>(p);
-  B200_LAUNCH_OK("tc_spmm_kernel");
-  return B200_OK;
+  return tc_run<KIND, false>(p, st.MB * NB, s);
 }
 
 // C = A_tiles * B (+ bias, ReLU).  ws: the plan's packed-operand workspace, its first 256 bytes zeroed once when
@@ -896,6 +980,115 @@ int launch_tc_forward(const TcStore& st, const int* row_ptr, const int* col, con
   return st.kind == KIND_F16
              ? tc_launch<KIND_F16>(st, row_ptr, col, val, B, ldb, N, C, ldc, bias, flags, ws, nt, s)
              : tc_launch<KIND_TF32>(st, row_ptr, col, val, B, ldb, N, C, ldc, bias, flags, ws, nt, s);
+}
+
+// ---- SDDMM on the tensor cores -------------------------------------------------------------------------------
+namespace {
+__global__ void tc_sample_mask_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M,
+                                      uint32_t* __restrict__ mask) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
+  for (int p = rs + lane; p < re; p += 32) {
+    const int c = __ldg(col + p);
+    atomicOr(mask + (size_t)(c >> 5) * M + row, 1u << (c & 31));
+  }
+}
+__global__ void tc_sample_off_kernel(const int* __restrict__ row_ptr, const uint32_t* __restrict__ mask, int M,
+                                     int groups, int* __restrict__ off) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  int q = __ldg(row_ptr + row);
+  for (int g = 0; g < groups; ++g) {  // [group][row]: coalesced across the rows of a warp
+    off[(size_t)g * M + row] = q;
+    q += __popc(mask[(size_t)g * M + row]);
+  }
+}
+}  // namespace
+
+void tc_sample_free(TcSample* sm) {
+  cudaFree(sm->mask); cudaFree(sm->off);
+  *sm = TcSample{};
+}
+
+// Pattern of a CSR matrix as per-(32-column group, row) bit masks + value offsets (rows sorted, no duplicates).
+int tc_sample_build(const int* row_ptr, const int* col, int M, int K, int nnz, TcSample* sm, cudaStream_t s) {
+  *sm = TcSample{};
+  sm->M = M; sm->K = K;
+  sm->groups = (K + 31) / 32;
+  const size_t cells = (size_t)sm->groups * (size_t)std::max(M, 1);
+  if (cells * 8 > ((size_t)4 << 30)) {
+    set_error("tensor-core SDDMM: pattern masks would take %zu bytes", cells * 8);
+    return B200_ERR_ALLOC;
+  }
+  B200_CUDA_OK(cudaMalloc(&sm->mask, cells * sizeof(uint32_t)));
+  B200_CUDA_OK(cudaMalloc(&sm->off, cells * sizeof(int)));
+  B200_CUDA_OK(cudaMemsetAsync(sm->mask, 0, cells * sizeof(uint32_t), s));
+  if (M > 0 && nnz > 0) {
+    tc_sample_mask_kernel<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, s>>>(row_ptr, col, M, sm->mask);
+    B200_LAUNCH_OK("tc_sample_mask_kernel");
+  }
+  if (M > 0) {
+    tc_sample_off_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(row_ptr, sm->mask, M, sm->groups, sm->off);
+    B200_LAUNCH_OK("tc_sample_off_kernel");
+  }
+  return B200_OK;
+}
+
+// workspace of the SDDMM: [control 256 B][row maxima of G][row maxima of B][packed G][packed B]
+size_t tc_sddmm_ws_bytes(int M, int K, int N, int nt, int kind) {
+  const size_t KT = (size_t)(N + bk_of(kind) - 1) / bk_of(kind);
+  const size_t NGa = (size_t)((M + BM - 1) / BM) * (BM / 8);
+  const size_t NGb = (size_t)((K + nt - 1) / nt) * (nt / 8);
+  return 256 + tc_colmax_bytes((int)NGa * 8) + tc_colmax_bytes((int)NGb * 8) + KT * (NGa + NGb) * ATOM;
+}
+
+template <int KIND>
+static int tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, const float* G, long long ldg,
+                    const float* B, long long ldb, int N, bool transposed, float* out, void* ws, int nt,
+                    cudaStream_t s) {
+  const int M = sm.M, K = sm.K;
+  const int KT = (N + bk_of(KIND) - 1) / bk_of(KIND);
+  const int MB = (M + BM - 1) / BM, NGa = MB * (BM / 8);
+  const int NB = (K + nt - 1) / nt, NGb = NB * (nt / 8);
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  int* ctl = reinterpret_cast<int*>(base);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(base + 256);
+  uint32_t* bmax = reinterpret_cast<uint32_t*>(base + 256 + tc_colmax_bytes(NGa * 8));
+  unsigned char* a_pack = base + 256 + tc_colmax_bytes(NGa * 8) + tc_colmax_bytes(NGb * 8);
+  unsigned char* b_pack = a_pack + (size_t)KT * NGa * ATOM;
+  // contraction over the dense column index n: G [M, N] / B [K, N] are [rows][depth]; the transposed forms
+  // (dy [N, M], x [N, K] of an FC layer) are [depth][rows]
+  int rc = tc_pack_operand<KIND>(G, ldg, M, N, /*by_depth=*/transposed, KT, NGa, a_pack, amax, ctl, s);
+  if (rc) return rc;
+  rc = tc_pack_operand<KIND>(B, ldb, K, N, /*by_depth=*/transposed, KT, NGb, b_pack, bmax, ctl, s);
+  if (rc) return rc;
+  TcParams p{};
+  p.a_tiles = a_pack; p.NGa = NGa; p.KT = KT;
+  p.b_pack = b_pack; p.NG = NGb;
+  p.C = out; p.M = M; p.N = N;
+  p.amax = amax; p.colmax = bmax;
+  p.samp_mask = sm.mask; p.samp_off = sm.off; p.groups = sm.groups;
+  p.MB = MB; p.NB = NB; p.Nt = nt;
+  p.ctl = ctl;
+  p.row_ptr = row_ptr; p.col = col;
+  p.G = G; p.g_sm = transposed ? 1 : ldg; p.g_sn = transposed ? ldg : 1;
+  p.B = B; p.b_sk = transposed ? 1 : ldb; p.b_sn = transposed ? ldb : 1;
+  return tc_run<KIND, true>(p, MB * NB, s);
+}
+
+// out[p] = sum_n G[row(p), n] * B[col(p), n] on the tensor cores (D = G * B^T sampled on the pattern).
+// transposed: G and B are given as [N, M] / [N, K] (gradient and activations of an FC layer as they are).
+int launch_tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, const float* G, long long ldg,
+                    const float* B, long long ldb, int N, bool transposed, float* out, void* ws, size_t ws_bytes,
+                    int nt, int kind, cudaStream_t s) {
+  if (sm.M == 0 || sm.K == 0) return B200_OK;
+  if (ws_bytes < tc_sddmm_ws_bytes(sm.M, sm.K, N, nt, kind)) {
+    set_error("tensor-core SDDMM: workspace too small");
+    return B200_ERR_INVALID;
+  }
+  return kind == KIND_F16 ? tc_sddmm<KIND_F16>(sm, row_ptr, col, G, ldg, B, ldb, N, transposed, out, ws, nt, s)
+                          : tc_sddmm<KIND_TF32>(sm, row_ptr, col, G, ldg, B, ldb, N, transposed, out, ws, nt, s);
 }
 
 }  // namespace b200

@@ -59,8 +59,12 @@ class _SparseLinear(torch.autograd.Function):
         M, K = csr.shape
         d_values = d_x = d_bias = None
         if ctx.needs_input_grad[0]:
-            # SDDMM takes G [out, tokens] and B [in, tokens]
-            d_values = plan.backward_A(g.t().contiguous(), x.t().contiguous())
+            if plan.would_use_tc(tokens, 2, 0):
+                # D = dy^T x on the tensor cores, sampled on W's pattern: dy [tokens, out] and x [tokens, in] as they are
+                d_values = plan.backward_A(g, x, _BT)
+            else:
+                # the gather SDDMM takes G [out, tokens] and B [in, tokens]
+                d_values = plan.backward_A(g.t().contiguous(), x.t().contiguous())
         if ctx.needs_input_grad[1]:
             if plan.would_use_tc(tokens, 1, 0):
                 d_x = torch.empty(tokens, K, device=g.device, dtype=torch.float32)

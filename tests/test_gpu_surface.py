@@ -285,11 +285,11 @@ def test_cusparsemm_on_a_csr_tensor_uses_the_inspected_plan(mods):
     one runs on the tensor-core tiles; forward and both gradients against fp64."""
     torch, custom_mm, matmuls = mods
     torch.manual_seed(7)
-    a = (torch.rand(384, 256, device="cuda") * (torch.rand(384, 256, device="cuda") < 0.2)).to_sparse_csr()
-    b = torch.rand(256, 96, device="cuda", requires_grad=True)
+    a = (torch.rand(1536, 1024, device="cuda") * (torch.rand(1536, 1024, device="cuda") < 0.2)).to_sparse_csr()
+    b = torch.rand(1024, 1024, device="cuda", requires_grad=True)
     a.requires_grad_(True)
     out = matmuls.cusparseMM.apply(a, b)
-    assert matmuls.as_csr(a).plan().last_path() == 1
+    assert matmuls.as_csr(a).plan().last_path() == 1  # large and dense enough: the cost model picks the tiles
     ad = a.detach().to_dense().double()
     ref = ad @ b.detach().double()
     assert float((out.double() - ref).abs().max() / ref.abs().max()) <= 1e-5

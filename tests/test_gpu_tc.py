@@ -224,20 +224,57 @@ def test_tc_plan_backward_and_value_refresh(kind):
     plan.close()
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("case", [(128, 64, 64, 0.3), (300, 260, 200, 0.15), (1000, 777, 500, 0.1), (129, 2100, 70, 0.2),
+                                  (640, 96, 4100, 0.25)])
+def test_tc_sddmm_on_the_pattern(case, kind):
+    """grad of the CSR values on the tensor cores (D = G B^T, contraction over the dense columns, sampled on A's
+    pattern by the epilogue), operands as [M, N] / [K, N] and transposed as [N, M] / [N, K]."""
+    import torch
+    M, K, N, dens = case
+    rng = np.random.default_rng(M + N)
+    rp, ci, va, _ = random_csr(rng, M, K, dens, heavy_rows=(0,), empty_rows=(1,))
+    G = rng.standard_normal((M, N)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    ref = oracle.sddmm_f64(rp, ci, (M, K), G, B)
+    crow, col, val, Gd, Bd = _dev(rp, ci, va, G, B)
+    capi.set_option("tc_kind", kind)
+    plan = capi.Plan(crow, col, val, (M, K))
+    out = plan.backward_A_ex(Gd, Bd, torch.full((len(va),), float("nan"), device="cuda:0"), flags=OP_FORCE_TC)
+    torch.cuda.synchronize()
+    assert plan.tc_timeout() == 0 and plan.tc_info()["last_path"] == 1
+    assert oracle.rel_err(out.cpu().numpy(), ref) <= TOL
+    out_t = plan.backward_A_ex(Gd.t().contiguous(), Bd.t().contiguous(),
+                               torch.full((len(va),), float("nan"), device="cuda:0"), flags=OP_FORCE_TC | OP_B_TRANSPOSED)
+    torch.cuda.synchronize()
+    assert oracle.rel_err(out_t.cpu().numpy(), ref) <= TOL
+    # Inf / NaN in an operand: the launch runs in CSR order and propagates them like the gather SDDMM
+    G2 = Gd.clone()
+    G2[3, 5] = float("inf")
+    o1 = plan.backward_A_ex(G2, Bd, torch.empty(len(va), device="cuda:0"), flags=OP_FORCE_TC)
+    o2 = plan.backward_A_ex(G2, Bd, torch.empty(len(va), device="cuda:0"), flags=OP_NO_TC)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.isfinite(o1), torch.isfinite(o2))
+    fin = torch.isfinite(o2)
+    assert float((o1[fin] - o2[fin]).abs().max()) <= 1e-5 * float(o2[fin].abs().max())
+    plan.close()
+
+
 def test_tc_auto_rule_picks_paths():
-    """Auto mode: dense-enough operands with N >= 32 take the tensor-core tiles, sparse or narrow ones the gather
-    kernels (crossover rule)."""
+    """Auto mode: large, dense-enough operands take the tensor-core tiles; sparse, small (launch-bound) or very narrow
+    ones the gather kernels (crossover rule: a cost model of both paths)."""
     import torch
     rng = np.random.default_rng(15)
-    for dens, N, want in ((0.10, 128, 1), (0.01, 128, 0), (0.10, 16, 0)):
-        rp, ci, va, _ = random_csr(rng, 512, 512, dens)
+    for S, dens, N, want in ((2048, 0.10, 512, 1), (2048, 0.01, 512, 0), (512, 0.10, 128, 0), (2048, 0.10, 4, 0)):
+        rp, ci, va, _ = random_csr(rng, S, S, dens)
         crow, col, val = _dev(rp, ci, va)
-        B, = _dev(rng.standard_normal((512, N)).astype(np.float32))
-        plan = capi.Plan(crow, col, val, (512, 512))
-        C = plan.forward(B, torch.empty(512, N, device="cuda:0"))
+        B, = _dev(rng.standard_normal((S, N)).astype(np.float32))
+        plan = capi.Plan(crow, col, val, (S, S))
+        C = plan.forward(B, torch.empty(S, N, device="cuda:0"))
         torch.cuda.synchronize()
-        assert plan.tc_info()["last_path"] == want, (dens, N)
-        assert oracle.rel_err(C.cpu().numpy(), oracle.spmm_f64(rp, ci, va, (512, 512), B.cpu().numpy())) <= TOL
+        assert plan.tc_info()["last_path"] == want, (S, dens, N)
+        assert plan.would_use_tc(N) == bool(want)
+        assert oracle.rel_err(C.cpu().numpy(), oracle.spmm_f64(rp, ci, va, (S, S), B.cpu().numpy())) <= TOL
         plan.close()
 
 

@@ -21,4 +21,10 @@ for _ in range(iters):
     plan.forward_ex(B, C, flags=OP_FORCE_TC)
 torch.cuda.synchronize()
 ref = A.double() @ B.double()
+if len(sys.argv) > 7 and sys.argv[7] == "sddmm":
+    G = torch.rand(M, N, device=dev, generator=g)
+    dv = torch.empty(val.numel(), device=dev)
+    for _ in range(iters):
+        plan.backward_A_ex(G, B, dv, flags=OP_FORCE_TC)
+    torch.cuda.synchronize()
 print("rel_err", float((C.double() - ref).abs().max() / ref.abs().max()), "timeout", plan.tc_timeout())
