@@ -255,11 +255,24 @@ def timed_region(fn_step, steps, warmup, dist, flush=None):
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
+    if flush is None:
+        # operands exceed L2: the K steps run back to back inside ONE event bracket (a bracket per step would expose
+        # ~3 us of launch latency per step, 3-4 % of a 0.09 ms multi-GPU step)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn_step()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            dist.barrier()
+        return e0.elapsed_time(e1), wall
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t0 = time.perf_counter()
     for i in range(steps):
-        if flush is not None:
-            flush()
+        flush()  # small operands: L2 flushed before every step, each step in its own event bracket
         ev[i][0].record()
         fn_step()
         ev[i][1].record()
@@ -398,14 +411,38 @@ def run_ours(args):
         capi.set_option(name, int(value))
 
     # ---- shard A's rows (nnz-balanced cost; one shard when world == 1) -----------------------------
-    bounds = sharding.shard_bounds(w["row_ptr"], world, N)
-    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
-    p0, p1 = int(w["row_ptr"][r0]), int(w["row_ptr"][r1])
-    crow = torch.from_numpy((w["row_ptr"][r0:r1 + 1] - p0).astype(np.int32)).to(dev)
-    col = torch.from_numpy(w["col"][p0:p1]).to(dev)
-    val = torch.from_numpy(w["val"][p0:p1]).to(dev)
     B_host = torch.from_numpy(w["B"]).pin_memory()
     B = B_host.to(dev)
+    bounds = sharding.shard_bounds(w["row_ptr"], world, N)
+    rebalance_log = []
+
+    def upload_shard(bounds):
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        p0, p1 = int(w["row_ptr"][r0]), int(w["row_ptr"][r1])
+        return (r0, r1, p0, p1, torch.from_numpy((w["row_ptr"][r0:r1 + 1] - p0).astype(np.int32)).to(dev),
+                torch.from_numpy(w["col"][p0:p1]).to(dev), torch.from_numpy(w["val"][p0:p1]).to(dev))
+
+    r0, r1, p0, p1, crow, col, val = upload_shard(bounds)
+    if world > 1 and not args.no_rebalance:
+        # inspector step of the multi-GPU plan: every rank times its own shard, the rows are re-cut from the measured
+        # times (sharding.rebalance_bounds), twice.  Outside the timed region, like plan creation.
+        for _ in range(2):
+            probe = capi.Plan(crow, col, val, (r1 - r0, K))
+            out_probe = torch.empty(r1 - r0, N, device=dev)
+            for _ in range(3):
+                probe.forward(B, out_probe)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                probe.forward(B, out_probe)
+            e1.record()
+            torch.cuda.synchronize()
+            ts = all_ranks(e0.elapsed_time(e1) / 10, dist)
+            probe.close()
+            del out_probe
+            rebalance_log.append({"shard_rows": [int(b) for b in bounds], "ms": [round(t, 5) for t in ts]})
+            bounds = sharding.rebalance_bounds(w["row_ptr"], bounds, ts, N)
+            r0, r1, p0, p1, crow, col, val = upload_shard(bounds)
     gather = sharding.RowGather(bounds, N, dev, dist) if world > 1 else None
     C_full = gather.buffer if gather is not None else torch.empty(M, N, device=dev)
     C_local = C_full[r0:r1]
@@ -673,7 +710,8 @@ def run_ours(args):
                    f"operands exceed L2 (B {K * N * 4 >> 20} MB, C {M * N * 4 >> 20} MB)",
                    "parallelism": (f"row-shard x{world} (cost-balanced on nnz and rows), B resident on every rank, C left "
                                    "row-sharded; 'gathered' = the same step + NCCL all-gather of C") if world > 1 else "single GPU",
-                   "shard_rows": [int(b) for b in bounds]},
+                   "shard_rows": [int(b) for b in bounds],
+                   "shard_rebalance": rebalance_log or None},
         "effective_gbs": round(algorithmic_bytes(w) / (ms_per_step * 1e-3) / 1e9, 1),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": args.traffic,
@@ -791,6 +829,7 @@ def main():
     ap.add_argument("--scale", type=int, default=None, help="R-MAT scale (c4) or matrix dimension (c5) override")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-comparators", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="keep the static cost-model shards at N > 1")
     ap.add_argument("--no-configs", action="store_true", help="skip the compact block of the other BASELINE configs")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (b200_set_option)")
     ap.add_argument("--traffic", type=float, default=None,

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -32,31 +33,34 @@ int device_sm_count() {
   return n;
 }
 
-// per-device scratch, grown on demand
+// scratch for the plan-less entry points when the caller passes no workspace: one buffer per (device, stream), grown on
+// demand.  Launches on one stream are ordered, so a buffer is never shared by concurrent work; growing it waits for
+// that stream only.  (Not usable under CUDA-graph capture: pass a workspace there.)
 static std::mutex g_scratch_mu;
-static void* g_scratch[64] = {nullptr};
-static size_t g_scratch_bytes[64] = {0};
+struct ScratchBuf { void* p = nullptr; size_t bytes = 0; };
+static std::map<std::pair<int, cudaStream_t>, ScratchBuf> g_scratch;
 
-int get_scratch(size_t bytes, void** ptr) {
+int get_scratch(size_t bytes, void** ptr, cudaStream_t stream) {
   int dev = 0;
   B200_CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_scratch_mu);
-  if (g_scratch_bytes[dev] < bytes) {
-    if (g_scratch[dev]) {
-      B200_CUDA_OK(cudaDeviceSynchronize());
-      B200_CUDA_OK(cudaFree(g_scratch[dev]));
-      g_scratch[dev] = nullptr;
-      g_scratch_bytes[dev] = 0;
+  ScratchBuf& sb = g_scratch[{dev, stream}];
+  if (sb.bytes < bytes) {
+    if (sb.p) {
+      B200_CUDA_OK(cudaStreamSynchronize(stream));
+      B200_CUDA_OK(cudaFree(sb.p));
+      sb.p = nullptr;
+      sb.bytes = 0;
     }
     size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
-    if (cudaMalloc(&g_scratch[dev], want) != cudaSuccess) {
+    if (cudaMalloc(&sb.p, want) != cudaSuccess) {
       cudaGetLastError();
       set_error("cudaMalloc of %zu scratch bytes failed", want);
       return B200_ERR_ALLOC;
     }
-    g_scratch_bytes[dev] = want;
+    sb.bytes = want;
   }
-  *ptr = g_scratch[dev];
+  *ptr = sb.p;
   return B200_OK;
 }
 
@@ -97,8 +101,12 @@ struct b200_plan {
   // owned scratch for forward / backward_B
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  // cached merge-path boundaries of A (fwd) and A^T (bwd), valid for the FwdPick stored beside them
-  void* bnd[2] = {nullptr, nullptr};
+  // cached merge-path boundaries of A (fwd) and A^T (bwd), valid for the FwdPick stored beside them: the task size
+  // depends on the number of column slabs (hence on N), so a plan keeps a few sets per side and products that
+  // alternate between widths do not re-partition
+  struct BndSet { void* part; FwdPick pick; };
+  std::vector<BndSet> bnd_sets[2];
+  void* bnd[2] = {nullptr, nullptr};   // the set selected for the current call
   FwdPick pick[2];
   bool bnd_valid[2] = {false, false};
   int* cnt[2] = {nullptr, nullptr};  // persistent arrival counters of split-row pieces (self-resetting)
@@ -125,23 +133,32 @@ struct b200_plan {
   size_t sd_ws_bytes = 0;
 };
 
-// Boundaries depend on (row_ptr, W, heavy) only: compute once per plan side, reuse for every N.
+// Boundaries depend on (row_ptr, W, heavy, tail split) only: computed once per distinct task shape, kept per side.
 static int plan_ensure_bounds(b200_plan* p, int side, const int* row_ptr, int M, int max_row, int64_t N,
                               cudaStream_t s) {
   FwdPick k = fwd_pick(M, p->nnz, N, true, true, max_row);
-  if (p->bnd_valid[side] && p->pick[side].W == k.W && p->pick[side].heavy == k.heavy &&
-      p->pick[side].n_tasks == k.n_tasks)
-    return B200_OK;
-  if (p->bnd[side]) {
-    B200_CUDA_OK(cudaStreamSynchronize(s));
-    B200_CUDA_OK(cudaFree(p->bnd[side]));
-    p->bnd[side] = nullptr;
-  }
   p->bnd_valid[side] = false;
   if (p->nnz == 0 || M == 0) return B200_OK;
-  B200_CUDA_OK(cudaMalloc(&p->bnd[side], fwd_bounds_bytes(k.n_tasks)));
-  int rc = launch_partition(row_ptr, M, p->nnz, k, p->bnd[side], s);
-  if (rc != B200_OK) return rc;
+  for (auto& e : p->bnd_sets[side]) {
+    if (e.pick.W == k.W && e.pick.heavy == k.heavy && e.pick.n_tasks == k.n_tasks && e.pick.t1 == k.t1 &&
+        e.pick.wf == k.wf) {
+      p->bnd[side] = e.part;
+      p->pick[side] = e.pick;
+      p->bnd_valid[side] = true;
+      return B200_OK;
+    }
+  }
+  if (p->bnd_sets[side].size() >= 8) {  // a plan used with many task shapes: drop the oldest set
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    B200_CUDA_OK(cudaFree(p->bnd_sets[side].front().part));
+    p->bnd_sets[side].erase(p->bnd_sets[side].begin());
+  }
+  void* part = nullptr;
+  B200_CUDA_OK(cudaMalloc(&part, fwd_bounds_bytes(k.n_tasks)));
+  int rc = launch_partition(row_ptr, M, p->nnz, k, part, s);
+  if (rc != B200_OK) { cudaFree(part); return rc; }
+  p->bnd_sets[side].push_back({part, k});
+  p->bnd[side] = part;
   p->pick[side] = k;
   p->bnd_valid[side] = true;
   return B200_OK;
@@ -255,6 +272,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
+  if (!strcmp(name, "tail_tasks")) { options().tail_tasks = (int)std::max<int64_t>(0, value); return B200_OK; }
   if (!strcmp(name, "d2c_warps")) {
     B200_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "d2c_warps must be 0, 2, 4, 8 or 16");
     options().d2c_warps = (int)value; return B200_OK;
@@ -277,6 +295,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "pipeline")) return options().pipeline;
   if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
+  if (!strcmp(name, "tail_tasks")) return options().tail_tasks;
   if (!strcmp(name, "d2c_warps")) return options().d2c_warps;
   if (!strcmp(name, "tc_mode")) return options().tc_mode;
   if (!strcmp(name, "tc_nt")) return options().tc_nt;
@@ -509,7 +528,9 @@ int b200_plan_create(const int32_t* d_row_ptr, const int32_t* d_col_ind, const f
 int b200_plan_destroy(b200_plan* p) {
   if (!p) return B200_OK;
   cudaFree(p->t_row_ptr); cudaFree(p->t_col); cudaFree(p->t_val); cudaFree(p->t_perm); cudaFree(p->ws);
-  cudaFree(p->bnd[0]); cudaFree(p->bnd[1]); cudaFree(p->sd_bnd); cudaFree(p->d_peers);
+  for (int side = 0; side < 2; ++side)
+    for (auto& e : p->bnd_sets[side]) cudaFree(e.part);
+  cudaFree(p->sd_bnd); cudaFree(p->d_peers);
   cudaFree(p->cnt[0]); cudaFree(p->cnt[1]);
   cudaFree(p->hB); cudaFree(p->hC); cudaFree(p->tc_ws); cudaFree(p->sd_ws);
   tc_sample_free(&p->samp);

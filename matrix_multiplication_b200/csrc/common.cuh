@@ -52,6 +52,7 @@ struct Options {
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
   int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
                            // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
+  int tail_tasks = 0;      // short tasks (W/4) at the end of a forward launch; measured no gain on config 4 and its shards (profiles/r2_scaling.md): off
   int d2c_warps = 0;       // dense->CSR one-pass tile size in warps (2, 4, 8, 16; 0 = default 4)
   // block-dense tensor-core path (tc_gemm.cu)
   int tc_mode = 1;         // 0 = never, 1 = auto (density / N rule), 2 = whenever the shape allows it
@@ -241,7 +242,18 @@ struct FwdParams {
   int stage;       // 1 / 0 force TMA staging on / off, -1 = process option
   const float* bias;  // optional [M]: added to every column of the finished row
   int relu;           // max(x, 0) on the finished row
+  // two task sizes: the first t1 tasks hold W items each, the rest wf <= W items (the tail of the launch drains in
+  // short tasks; set from FwdPick by the launcher)
+  int t1, wf;
 };
+// first merge-path item of task t / task that holds item i, for W-item tasks followed by wf-item tasks
+__host__ __device__ __forceinline__ long long task_first_item(long long t, int W, int t1, int wf) {
+  return t <= t1 ? t * W : (long long)t1 * W + (t - t1) * wf;
+}
+__host__ __device__ __forceinline__ long long task_of_item(long long i, int W, int t1, int wf) {
+  const long long coarse = (long long)t1 * W;
+  return i < coarse ? i / W : t1 + (i - coarse) / wf;
+}
 // multi-GPU epilogue (row-sharded A): every finished row of C is also stored into the same row block of
 // the other ranks' buffers — plain P2P stores to mapped peer pointers, or one multimem.st to an NVLS
 // multicast address that the NVSwitch replicates to every rank (including this one).  Kept out of
@@ -264,6 +276,7 @@ struct PeerArg<false> {
 // lane layout + task size chosen for a problem (spmm_fwd.cu)
 struct FwdPick {
   int vec, lpr, W, heavy, n_tasks, slabs;
+  int t1, wf;  // the first t1 tasks hold W items, the remaining ones wf
   bool may_split;  // false when no row is longer than `heavy`: no pieces, no fix-up launch
 };
 FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool aligned2, int max_row);
@@ -331,7 +344,7 @@ int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, in
                         long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,
                         const float* bias, bool relu, cudaStream_t s);
 
-// per-device cached scratch (grown on demand; stream-ordered use only)
-int get_scratch(size_t bytes, void** ptr);
+// cached scratch per (device, stream), grown on demand
+int get_scratch(size_t bytes, void** ptr, cudaStream_t stream);
 
 }  // namespace b200

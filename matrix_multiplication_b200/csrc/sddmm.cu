@@ -366,7 +366,7 @@ int launch_sddmm(const int* row_ptr, const int* col, int M, int nnz, const float
   const Boundary* bnd = cached_bnd;
   if (bnd == nullptr) {
     void* w = nullptr;
-    int rc = get_scratch(sddmm_bounds_bytes(M, nnz), &w);
+    int rc = get_scratch(sddmm_bounds_bytes(M, nnz), &w, s);
     if (rc != B200_OK) return rc;
     rc = launch_sddmm_partition(row_ptr, M, nnz, reinterpret_cast<Boundary*>(w), s);
     if (rc != B200_OK) return rc;

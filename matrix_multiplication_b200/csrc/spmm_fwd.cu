@@ -41,11 +41,12 @@ __host__ __device__ inline const Boundary* part_bnd(const void* part) {
 }
 
 __global__ void __launch_bounds__(256)
-partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int heavy, int n_tasks,
+partition_kernel(const int* __restrict__ row_ptr, int M, int nnz, int W, int heavy, int n_tasks, int t1, int wf,
                  void* __restrict__ part) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tasks) return;
-  const_cast<Boundary*>(part_bnd(part))[t] = merge_path_boundary(row_ptr, M, nnz, (long long)t * W, heavy);
+  const_cast<Boundary*>(part_bnd(part))[t] =
+      merge_path_boundary(row_ptr, M, nnz, t == n_tasks ? (long long)M + nnz : task_first_item(t, W, t1, wf), heavy);
 }
 
 // A finished row slab of C: local store, plus the multi-GPU epilogue (peer stores / multicast store).
@@ -90,9 +91,9 @@ __device__ __forceinline__ void piece_done(const FwdParams& p, const PeerArg<PEE
                                            bool reader, int lane) {
   const long long first_item = (long long)__ldg(p.row_ptr + row) + row;
   const long long end_item = (long long)__ldg(p.row_ptr + row + 1) + row;  // the row-end item
-  const int t_first = (int)(first_item / W);
-  int t_end = (int)(end_item / W);
-  if (end_item % W == 0) --t_end;  // a boundary on a row-end item is moved past it (merge_path_boundary)
+  const int t_first = (int)task_of_item(first_item, W, p.t1, p.wf);
+  int t_end = (int)task_of_item(end_item, W, p.t1, p.wf);
+  if (end_item == task_first_item(t_end, W, p.t1, p.wf)) --t_end;  // a boundary on a row-end item is moved past it
   const int n_pieces = t_end - t_first + 1;
   int* cnt = p.counters + (size_t)t_end * gridDim.y + blockIdx.y;
   __threadfence();  // this lane's piece is visible device-wide before the count moves
@@ -627,7 +628,15 @@ FwdPick fwd_pick(long long M, long long nnz, long long N, bool aligned4, bool al
   k.W = W;
   k.heavy = W;
   const long long items = M + nnz;
-  k.n_tasks = (int)((items + W - 1) / W);
+  // The launch ends when its slowest warp does, and a W-item task is a serial chain of W/8 gather batches (~20 us at
+  // W = 256): the last items are cut into short tasks (W/4) so that the tail drains in a quarter of that.  Fine
+  // region: about two waves of resident warps, at most a quarter of the items.
+  k.wf = std::max(32, (W / 4 + 31) & ~31);
+  long long fine_items = std::min<long long>(items / 4, (long long)options().tail_tasks * k.wf);
+  if (options().tail_tasks <= 0 || k.wf >= W) fine_items = 0;
+  k.t1 = (int)((items - fine_items + W - 1) / W);
+  const long long rest = std::max<long long>(0, items - (long long)k.t1 * W);
+  k.n_tasks = k.t1 + (int)((rest + k.wf - 1) / k.wf);
   if (k.n_tasks < 1) k.n_tasks = 1;
   k.slabs = (int)((N + (long long)k.lpr * k.vec - 1) / ((long long)k.lpr * k.vec));
   k.may_split = (max_row < 0) || (max_row > k.heavy);
@@ -654,7 +663,7 @@ size_t fwd_workspace_bytes(long long M, long long nnz, long long N) {
 
 int launch_partition(const int* row_ptr, int M, int nnz, const FwdPick& k, void* part, cudaStream_t s) {
   const int n = k.n_tasks + 1;
-  partition_kernel<<<(n + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, k.W, k.heavy, k.n_tasks, part);
+  partition_kernel<<<(n + 255) / 256, 256, 0, s>>>(row_ptr, M, nnz, k.W, k.heavy, k.n_tasks, k.t1, k.wf, part);
   B200_LAUNCH_OK("partition_kernel");
   return B200_OK;
 }
@@ -680,7 +689,10 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
   const bool a2 = is_aligned(p.B, 8) && is_aligned(p.C, 8) && (p.ldb % 2 == 0) && (p.ldc % 2 == 0);
   FwdPick k = fwd_pick(p.M, p.nnz, p.N, a4, a2, -1);
   const bool use_cache = cached_part != nullptr && cached_pick != nullptr && cached_pick->W == k.W &&
-                         cached_pick->heavy == k.heavy && cached_pick->n_tasks == k.n_tasks;
+                         cached_pick->heavy == k.heavy && cached_pick->n_tasks == k.n_tasks &&
+                         cached_pick->t1 == k.t1 && cached_pick->wf == k.wf;
+  p.t1 = k.t1;
+  p.wf = k.wf;
   if (use_cache) k.may_split = cached_pick->may_split;
   const size_t part_bytes = use_cache ? 0 : fwd_bounds_bytes(k.n_tasks);
   const size_t pieces_bytes =
@@ -689,7 +701,7 @@ int launch_spmm_forward(const FwdParams& pin, void* workspace, size_t workspace_
   const size_t need = part_bytes + pieces_bytes + counter_bytes;
   if (workspace == nullptr && need > 0) {
     void* w = nullptr;
-    int rc = get_scratch(need, &w);
+    int rc = get_scratch(need, &w, s);
     if (rc != B200_OK) return rc;
     workspace = w;
     workspace_bytes = need;
