@@ -226,6 +226,28 @@ static int plan_ensure_transpose(b200_plan* p, cudaStream_t s) {
 namespace {
 __global__ void smoke_kernel() {}
 
+// Column panel of a row-major matrix copied by SMs instead of the copy engine: `rows` rows of `w4` 16-byte vectors,
+// both sides with the same pitch.  One side is pinned host memory (mapped into the device address space): the SMs
+// issue 16-byte loads / stores straight over PCIe, 128-512 bytes per row segment per warp.  A 2-D DMA with 256-byte
+// rows runs well below the link rate; this does not care about the row length.
+__global__ void __launch_bounds__(256)
+panel_copy_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long long rows, int w4, long long pitch4) {
+  const long long total = rows * w4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / w4;
+    const int c = (int)(i - r * w4);
+    dst[r * pitch4 + c] = src[r * pitch4 + c];
+  }
+}
+
+// device-visible alias of a pinned host buffer (nullptr for pageable memory)
+const void* device_alias(const void* host) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
+
 struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
@@ -272,6 +294,8 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
+  if (!strcmp(name, "host_copy_mode")) { options().host_copy_mode = (int)value; return B200_OK; }
+  if (!strcmp(name, "host_copy_ctas")) { options().host_copy_ctas = (int)value; return B200_OK; }
   if (!strcmp(name, "tail_tasks")) { options().tail_tasks = (int)std::max<int64_t>(0, value); return B200_OK; }
   if (!strcmp(name, "d2c_warps")) {
     B200_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "d2c_warps must be 0, 2, 4, 8 or 16");
@@ -295,6 +319,8 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "pipeline")) return options().pipeline;
   if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
+  if (!strcmp(name, "host_copy_mode")) return options().host_copy_mode;
+  if (!strcmp(name, "host_copy_ctas")) return options().host_copy_ctas;
   if (!strcmp(name, "tail_tasks")) return options().tail_tasks;
   if (!strcmp(name, "d2c_warps")) return options().d2c_warps;
   if (!strcmp(name, "tc_mode")) return options().tc_mode;
@@ -793,11 +819,24 @@ int b200_plan_forward_host(b200_plan* p, const float* h_B, int64_t N, float* h_C
     for (int i = 0; i < panels; ++i)
       if (!p->hev[j][i]) B200_CUDA_OK(cudaEventCreateWithFlags(&p->hev[j][i], cudaEventDisableTiming));
   const size_t pitch = (size_t)N * sizeof(float);
+  // SM-driven panel copies when both host buffers are pinned (mapped) and 16-byte friendly; the copy engine otherwise
+  const float* dB = reinterpret_cast<const float*>(device_alias(h_B));
+  float* dC = reinterpret_cast<float*>(const_cast<void*>(device_alias(h_C)));
+  const bool sm_copy = options().host_copy_mode == 1 && panels > 1 && dB != nullptr && dC != nullptr && N % 4 == 0 &&
+                       w % 4 == 0 && reinterpret_cast<uintptr_t>(dB) % 16 == 0 && reinterpret_cast<uintptr_t>(dC) % 16 == 0;
+  const int copy_ctas = std::max(16, options().host_copy_ctas);
   for (int i = 0; i < panels; ++i) {
     const size_t off = (size_t)i * w;
     if (p->nnz > 0) {
-      B200_CUDA_OK(cudaMemcpy2DAsync(p->hB + off, pitch, h_B + off, pitch, (size_t)w * sizeof(float), (size_t)p->K,
-                                     cudaMemcpyHostToDevice, p->hs[0]));
+      if (sm_copy) {
+        panel_copy_kernel<<<copy_ctas, 256, 0, p->hs[0]>>>(reinterpret_cast<float4*>(p->hB + off),
+                                                          reinterpret_cast<const float4*>(dB + off), p->K, (int)(w / 4),
+                                                          N / 4);
+        B200_LAUNCH_OK("panel_copy_kernel");
+      } else {
+        B200_CUDA_OK(cudaMemcpy2DAsync(p->hB + off, pitch, h_B + off, pitch, (size_t)w * sizeof(float), (size_t)p->K,
+                                       cudaMemcpyHostToDevice, p->hs[0]));
+      }
     }
     B200_CUDA_OK(cudaEventRecord(p->hev[0][i], p->hs[0]));
     B200_CUDA_OK(cudaStreamWaitEvent(p->hs[1], p->hev[0][i], 0));
@@ -806,8 +845,15 @@ int b200_plan_forward_host(b200_plan* p, const float* h_B, int64_t N, float* h_C
     if (rc) return rc;
     B200_CUDA_OK(cudaEventRecord(p->hev[1][i], p->hs[1]));
     B200_CUDA_OK(cudaStreamWaitEvent(p->hs[2], p->hev[1][i], 0));
-    B200_CUDA_OK(cudaMemcpy2DAsync(h_C + off, pitch, p->hC + off, pitch, (size_t)w * sizeof(float), (size_t)p->M,
-                                   cudaMemcpyDeviceToHost, p->hs[2]));
+    if (sm_copy) {
+      panel_copy_kernel<<<copy_ctas, 256, 0, p->hs[2]>>>(reinterpret_cast<float4*>(dC + off),
+                                                        reinterpret_cast<const float4*>(p->hC + off), p->M, (int)(w / 4),
+                                                        N / 4);
+      B200_LAUNCH_OK("panel_copy_kernel");
+    } else {
+      B200_CUDA_OK(cudaMemcpy2DAsync(h_C + off, pitch, p->hC + off, pitch, (size_t)w * sizeof(float), (size_t)p->M,
+                                     cudaMemcpyDeviceToHost, p->hs[2]));
+    }
   }
   B200_CUDA_OK(cudaStreamSynchronize(p->hs[2]));
   return B200_OK;

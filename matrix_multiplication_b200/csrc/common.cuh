@@ -52,6 +52,8 @@ struct Options {
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
   int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
                            // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
+  int host_copy_mode = 0;  // b200_plan_forward_host panel copies: 0 = copy engine (cudaMemcpy2DAsync), 1 = SM copy kernel
+  int host_copy_ctas = 32; // CTAs of one SM-driven panel copy
   int tail_tasks = 0;      // short tasks (W/4) at the end of a forward launch; measured no gain on config 4 and its shards (profiles/r2_scaling.md): off
   int d2c_warps = 0;       // dense->CSR one-pass tile size in warps (2, 4, 8, 16; 0 = default 4)
   // block-dense tensor-core path (tc_gemm.cu)
