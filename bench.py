@@ -368,7 +368,7 @@ def run_config_block(dev, peak):
         plan.forward(B, C)
         t = timeit(lambda: plan.forward(B, C))
         by = synthetic.spmm_algorithmic_bytes(M, K, nnz, N)
-        r = {"config": label, "nnz": nnz, "path": ["gather kernels", "tensor-core tiles", "strided"][plan.tc_info()["last_path"]],
+        r = {"config": label, "nnz": nnz, "path": ["gather kernels", "tensor-core tiles", "strided", "smem slabs"][plan.tc_info()["last_path"]],
              "fwd_ms": round(t, 5), "gflops": round(2.0 * nnz * N / t / 1e6, 1),
              "frac_of_hbm_roof": round(by / t / 1e6 / peak, 4)}
         try:

@@ -6,7 +6,8 @@
 
 Arms (same weights, same inputs, CUDA-event timing of forward + loss.sum().backward(), median of --iters):
   engine        matrix_multiplication_b200.layers.cusparseLinear (persistent CSR weight, cached transpose, SDDMM grad)
-  engine_T      same, activations kept transposed between the layers (forward_t), no transposes inside the step
+  engine_fused  same with the ReLU of the first layer fused into its product (cusparseLinear(activation='relu'));
+                also replayed from a CUDA graph (launch-bound configs: one launch per step)
   torch_sparse  torch.sparse.mm on a CSR weight (cuSPARSE forward; torch's own sparse backward)
   dense         nn.Linear on the densified weights (cuBLAS SGEMM fp32)
   reference     the reference's cusparse FC layer call, `cusparseMM.apply(inp, weight.t())`
@@ -67,6 +68,7 @@ def main():
         torch.manual_seed(0)
         l1 = cusparseLinear(dims[0], dims[1], sparsity=0.9, seed=1).to(dev)
         l2 = cusparseLinear(dims[1], dims[2], sparsity=0.9, seed=2).to(dev)
+        f1 = cusparseLinear(dims[0], dims[1], sparsity=0.9, seed=1, activation="relu").to(dev)  # same weights as l1
         x = torch.rand(tokens, dims[0], device=dev)
         xT = x.t().contiguous()
         nnz = l1.values.numel() + l2.values.numel()
@@ -78,9 +80,9 @@ def main():
             l2(torch.relu(l1(x))).sum().backward()
 
         def step_engine_t():
-            for p in (l1.values, l2.values, l1.bias, l2.bias):
+            for p in (f1.values, l2.values, f1.bias, l2.bias):
                 p.grad = None
-            l2.forward_t(torch.relu(l1.forward_t(xT))).sum().backward()
+            l2(f1(x)).sum().backward()
 
         t1, t2 = TorchSparseLinear(l1).to(dev), TorchSparseLinear(l2).to(dev)
 
@@ -106,7 +108,7 @@ def main():
         r = {"config": name, "nnz": nnz, "tokens": tokens, "rel_diff_vs_dense": rel}
         # the same engine step captured once in a CUDA graph and replayed (launch-bound configs: one launch per step)
         try:
-            for p in (l1.values, l2.values, l1.bias, l2.bias):
+            for p in (f1.values, l2.values, f1.bias, l2.bias):
                 p.grad = None
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -114,28 +116,29 @@ def main():
                 for _ in range(3):
                     step_engine_t()
             torch.cuda.current_stream().wait_stream(side)
-            for p in (l1.values, l2.values, l1.bias, l2.bias):
+            for p in (f1.values, l2.values, f1.bias, l2.bias):
                 p.grad = None
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                l2.forward_t(torch.relu(l1.forward_t(xT))).sum().backward()
+                l2(f1(x)).sum().backward()
             graph.replay()
             torch.cuda.synchronize()
-            g_graph = l1.values.grad.clone()
+            g_graph = f1.values.grad.clone()
             step_engine_t()
-            r["graph_grad_rel_diff"] = float((g_graph - l1.values.grad).abs().max() / l1.values.grad.abs().max())
-            r["engine_T_graph_ms"] = timeit(graph.replay, args.iters)
+            r["graph_grad_rel_diff"] = float((g_graph - f1.values.grad).abs().max() / f1.values.grad.abs().max())
+            r["engine_fused_graph_ms"] = timeit(graph.replay, args.iters)
         except Exception as e:
-            r["engine_T_graph_error"] = f"{type(e).__name__}: {str(e)[:160]}"
+            r["engine_fused_graph_error"] = f"{type(e).__name__}: {str(e)[:160]}"
         r["engine_ms"] = timeit(step_engine, args.iters)
-        r["engine_T_ms"] = timeit(step_engine_t, args.iters)
+        r["engine_fused_ms"] = timeit(step_engine_t, args.iters)
+        r["paths"] = {"fc1": l1.csr().plan().last_path(), "fc2": l2.csr().plan().last_path()}
         try:
             r["torch_sparse_ms"] = timeit(step_torch_sparse, args.iters)
         except Exception as e:
             r["torch_sparse_ms"] = None
             r["torch_sparse_error"] = str(e)[:100]
         r["dense_ms"] = timeit(step_dense, args.iters)
-        r["engine_gflops"] = flops / r["engine_T_ms"] / 1e6
+        r["engine_gflops"] = flops / r["engine_fused_ms"] / 1e6
         try:
             from oracle import build_ref
             rcm, rmm = build_ref.load()

@@ -132,7 +132,7 @@ def main():
         by_a = synthetic.sddmm_algorithmic_bytes(M, K, nnz, N)
         t = timeit(lambda: plan.forward(B, C, stream=stream), args.iters, flush)
         r["fwd_ms"], r["fwd_gflops"], r["fwd_gbs"], r["fwd_frac"] = t, fl / t / 1e6, by_f / t / 1e6, by_f / t / 1e6 / PEAK
-        r["fwd_path"] = ["gather", "tensor-core tiles", "strided"][plan.tc_info()["last_path"]]
+        r["fwd_path"] = ["gather", "tensor-core tiles", "strided", "smem slabs"][plan.tc_info()["last_path"]]
         r["fwd_warm_ms"] = timeit_warm(lambda: plan.forward(B, C, stream=stream), args.iters * 2)
         if r["fwd_path"] != "gather":  # the gather kernels on the same operand, for the crossover table
             from matrix_multiplication_b200._capi import OP_NO_TC

@@ -71,6 +71,7 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  * items_per_task: merge-path items (row ends + non-zeros) per warp task; 0 = auto (256, less for small problems).
  * pipeline      : forward kernel variant, 0 = shipped (profiles/r1_variant_sweep.md lists the alternatives).
  * flat_min_n    : smallest N served by the one-lane-group kernel (default 24; below it lane groups share a warp).
+ * slab_mode     : narrow-N (4 / 8 / 16 columns) shared-memory slab kernel: 0 never, 1 auto (default).
  * tc_mode       : block-dense tensor-core path: 0 never, 1 auto (default), 2 whenever the shape allows it.
  * tc_min_density_pct : auto rule floor, nnz / (M*K) in percent (default 2); above it a measured cost model of the two
  *                 paths decides (small or very sparse problems stay on the gather kernels).
@@ -221,7 +222,8 @@ int b200_plan_backward_B_ex(b200_plan* plan, const float* d_G, int64_t ldg, int6
 /* grad of the CSR values with the same path choice: on dense-enough operands D = G * B^T runs on the tensor-core tiles
  * (both operands packed per call, contraction over the N dense columns) and the epilogue writes only the entries on
  * A's pattern.  B200_OP_B_TRANSPOSED: BOTH operands are given transposed, d_G as [N, M] and d_B as [N, K] (the
- * gradient and the activations of an FC layer as they are; tensor-core path only). */
+ * gradient and the activations of an FC layer as they are; served by the tiles, or by a plain CSR-order kernel that is
+ * only meant for small problems). */
 int b200_plan_backward_A_ex(b200_plan* plan, const float* d_G, int64_t ldg, const float* d_B, int64_t ldb, int64_t N,
                             float* d_dval, uint32_t flags, void* stream);
 /* 1 if a product with N dense columns over this side of the plan (0 = A: forward, 1 = A^T: backward_B, 2 = the SDDMM
@@ -230,7 +232,7 @@ int b200_plan_backward_A_ex(b200_plan* plan, const float* d_G, int64_t ldg, cons
  * to pass them as they are (B200_OP_*_TRANSPOSED are served efficiently by the tiles only). */
 int b200_plan_would_use_tc(const b200_plan* plan, int side, int64_t N, uint32_t flags);
 /* Block-dense state of a plan side (0 = A, 1 = A^T): stored tiles, their bytes, and the path the last product took
- * (0 gather kernels, 1 tensor-core tiles, 2 strided fallback). */
+ * (0 gather kernels, 1 tensor-core tiles, 2 strided fallback, 3 shared-memory slab kernel for narrow N). */
 int b200_plan_tc_info(const b200_plan* plan, int side, int64_t* n_tiles, int64_t* tile_bytes, int* last_path);
 /* Debug aid: non-zero when a pipeline wait of the last tensor-core launch gave up (protocol bug); synchronises. */
 int b200_tc_last_timeout(const b200_plan* plan, int* code);

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
-CU_SOURCES = ["capi.cu", "spmm_fwd.cu", "sddmm.cu", "transpose.cu", "dense_to_csr.cu", "tc_gemm.cu"]
+CU_SOURCES = ["capi.cu", "spmm_fwd.cu", "sddmm.cu", "transpose.cu", "dense_to_csr.cu", "tc_gemm.cu", "spmm_slab.cu"]
 
 
 def _nvcc() -> str:

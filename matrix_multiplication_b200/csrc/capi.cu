@@ -127,6 +127,8 @@ struct b200_plan {
   void* tc_ws = nullptr;               // [non-finite flag | debug word | packed dense operand]
   size_t tc_ws_bytes = 0;
   int last_path = 0;                   // 0 gather kernels, 1 tensor-core tiles, 2 strided fallback
+  SlabStore slab[2];                   // narrow-N slab kernel state per side (built for one N at a time)
+  bool slab_built[2] = {false, false};
   TcSample samp;                       // A's pattern as bit masks, for the tensor-core SDDMM's sampling epilogue
   bool samp_built = false, samp_failed = false;
   void* sd_ws = nullptr;               // packed G and B of the tensor-core SDDMM
@@ -294,6 +296,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "items_per_task")) { options().items_per_task = (int)value; return B200_OK; }
   if (!strcmp(name, "pipeline")) { options().pipeline = (int)value; return B200_OK; }
   if (!strcmp(name, "flat_min_n")) { options().flat_min_n = (int)value; return B200_OK; }
+  if (!strcmp(name, "slab_mode")) { options().slab_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "host_copy_mode")) { options().host_copy_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "host_copy_ctas")) { options().host_copy_ctas = (int)value; return B200_OK; }
   if (!strcmp(name, "tail_tasks")) { options().tail_tasks = (int)std::max<int64_t>(0, value); return B200_OK; }
@@ -319,6 +322,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "pipeline")) return options().pipeline;
   if (!strcmp(name, "flat_min_n")) return options().flat_min_n;
+  if (!strcmp(name, "slab_mode")) return options().slab_mode;
   if (!strcmp(name, "host_copy_mode")) return options().host_copy_mode;
   if (!strcmp(name, "host_copy_ctas")) return options().host_copy_ctas;
   if (!strcmp(name, "tail_tasks")) return options().tail_tasks;
@@ -560,6 +564,7 @@ int b200_plan_destroy(b200_plan* p) {
   cudaFree(p->cnt[0]); cudaFree(p->cnt[1]);
   cudaFree(p->hB); cudaFree(p->hC); cudaFree(p->tc_ws); cudaFree(p->sd_ws);
   tc_sample_free(&p->samp);
+  slab_store_free(&p->slab[0]); slab_store_free(&p->slab[1]);
   tc_store_free(&p->tc[0]); tc_store_free(&p->tc[1]);
   for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
   for (int j = 0; j < 2; ++j) for (int i = 0; i < 16; ++i) if (p->hev[j][i]) cudaEventDestroy(p->hev[j][i]);
@@ -640,7 +645,9 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
 //                      tile bytes (x column blocks when they exceed L2) / 5.5e6 B per us,
 //                      6 * M_pad * K * N_pad / R, R = 1.3e9 (fp16 split) or 0.65e9 (tf32 split) flop per us
 // so small problems stay on the gather kernels (launch-bound: config 1-2), and large ones switch at ~4-5 % density.
+static double g_last_tc_estimate_us = 0.0;  // the tiles' estimated time of the last plan_wants_tc() call (same thread)
 static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t flags, bool sddmm = false) {
+  g_last_tc_estimate_us = 1e30;
   if (flags & B200_OP_NO_TC) return false;
   const int mode = options().tc_mode;
   if (mode == 0 && !(flags & B200_OP_FORCE_TC)) return false;
@@ -668,6 +675,7 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
     return t_t < t_g;
   }
   const double t_tc = 28.0 + std::max(t_stream, t_mma);
+  g_last_tc_estimate_us = t_tc;
   return t_tc < t_gather;
 }
 
@@ -707,7 +715,12 @@ static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* c
   B200_REQUIRE(d_C != nullptr && (p->nnz == 0 || d_B != nullptr), "null B / C");
   int rc = plan_check_device(p);
   if (rc) return rc;
-  if (plan_wants_tc(p, M, K, N, flags)) {
+  bool want_tc = plan_wants_tc(p, M, K, N, flags);
+  // narrow dense operand whose rows fit a few shared-memory slabs: ~15 us + nnz / 4.0e5 us on the slab kernel
+  const bool slab_ok = !bt && !ct && options().slab_mode == 1 && !(flags & B200_OP_FORCE_TC) &&
+                       slab_wanted(M, K, p->nnz, (int)N, d_B, ldb, d_C, ldc);
+  if (slab_ok && want_tc && 15.0 + (double)p->nnz / 4.0e5 < g_last_tc_estimate_us) want_tc = false;
+  if (want_tc) {
     rc = plan_ensure_tc(p, side, row_ptr, col, val, M, K, s);
     if (rc == B200_OK) {
       const int nt = options().tc_nt > 0 ? options().tc_nt : tc_pick_nt(p->tc[side].MB, (int)N, device_sm_count());
@@ -734,6 +747,17 @@ static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* c
     p->last_path = 2;
     return launch_spmm_strided(row_ptr, col, val, M, (int)N, d_B, bt ? 1 : ldb, bt ? ldb : 1, d_C, ct ? 1 : ldc,
                                ct ? ldc : 1, d_bias, relu, s);
+  }
+  if (slab_ok) {
+    // gather from shared-memory slabs of B instead of L1 / L2
+    if (!p->slab_built[side] || p->slab[side].N != (int)N) {
+      if (p->slab_built[side]) { B200_CUDA_OK(cudaStreamSynchronize(s)); slab_store_free(&p->slab[side]); p->slab_built[side] = false; }
+      rc = slab_store_build(row_ptr, col, M, K, p->nnz, (int)N, &p->slab[side], s);
+      if (rc) return rc;
+      p->slab_built[side] = true;
+    }
+    p->last_path = 3;
+    return launch_spmm_slab(p->slab[side], col, val, d_B, d_C, ldc, d_bias, relu ? 1 : 0, s);
   }
   p->last_path = 0;
   return plan_spmm(p, side, row_ptr, col, val, M, K, max_row, d_B, ldb, N, d_C, ldc, s, nullptr, 0, nullptr, d_bias,
@@ -916,7 +940,10 @@ static int plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const fl
     }
     if (flags & B200_OP_FORCE_TC) return rc;
   }
-  B200_REQUIRE(!tr, "transposed SDDMM operands need the tensor-core path (b200_plan_would_use_tc)");
+  if (tr) {  // operands held transposed on a matrix that is too sparse / small for the tiles: plain CSR-order kernel
+    p->last_path = 2;
+    return launch_sddmm_strided(p->row_ptr, p->col, p->M, (int)N, d_G, 1, ldg, d_B, 1, ldb, d_dval, s);
+  }
   if (p->sd_bnd == nullptr) {
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p->sd_bnd), sddmm_bounds_bytes(p->M, p->nnz)));
     int rc = launch_sddmm_partition(p->row_ptr, p->M, p->nnz, p->sd_bnd, s);

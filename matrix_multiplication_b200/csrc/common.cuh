@@ -52,6 +52,7 @@ struct Options {
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
   int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
                            // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
+  int slab_mode = 1;       // narrow-N shared-memory slab kernel: 0 = never, 1 = when slab_wanted() says so
   int host_copy_mode = 0;  // b200_plan_forward_host panel copies: 0 = copy engine (cudaMemcpy2DAsync), 1 = SM copy kernel
   int host_copy_ctas = 32; // CTAs of one SM-driven panel copy
   int tail_tasks = 0;      // short tasks (W/4) at the end of a forward launch; measured no gain on config 4 and its shards (profiles/r2_scaling.md): off
@@ -329,6 +330,17 @@ size_t tc_pack_b_bytes(int K, int N, int nt, int kind);
 int launch_tc_forward(const TcStore& st, const int* row_ptr, const int* col, const float* val, const float* B,
                       long long ldb, int N, float* C, long long ldc, const float* bias, unsigned flags, void* ws,
                       size_t ws_bytes, int nt, cudaStream_t s);
+// narrow-N forward over shared-memory slabs of B (spmm_slab.cu)
+struct SlabStore {
+  int N = 0, M = 0, K = 0, S = 0, rows_per_slab = 0, G = 0;
+  int* slab_ptr = nullptr;  // [M][S + 1] first non-zero of a row at or beyond every slab boundary
+  int* cta_rows = nullptr;  // [G + 1] first row of every persistent CTA
+};
+bool slab_wanted(int M, int K, long long nnz, int N, const float* B, long long ldb, const float* C, long long ldc);
+int slab_store_build(const int* row_ptr, const int* col, int M, int K, int nnz, int N, SlabStore* st, cudaStream_t s);
+void slab_store_free(SlabStore* st);
+int launch_spmm_slab(const SlabStore& st, const int* col, const float* val, const float* B, float* C, long long ldc,
+                     const float* bias, int relu, cudaStream_t s);
 // pattern of a CSR matrix for the tensor-core SDDMM's sampling epilogue
 struct TcSample {
   int M = 0, K = 0, groups = 0;
@@ -341,6 +353,8 @@ size_t tc_sddmm_ws_bytes(int M, int K, int N, int nt, int kind);
 int launch_tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, const float* G, long long ldg,
                     const float* B, long long ldb, int N, bool transposed, float* out, void* ws, size_t ws_bytes,
                     int nt, int kind, cudaStream_t s);
+int launch_sddmm_strided(const int* row_ptr, const int* col, int M, int N, const float* G, long long g_sm,
+                         long long g_sn, const float* B, long long b_sk, long long b_sn, float* out, cudaStream_t s);
 // generic strided CSR SpMM (any B / C strides, bias, ReLU): the correctness fallback of the extended forward
 int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, int M, int N, const float* B,
                         long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,

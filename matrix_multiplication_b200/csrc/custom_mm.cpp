@@ -81,9 +81,14 @@ torch::Tensor spmm_into(const torch::Tensor& values, const torch::Tensor& column
 // ---- the reference's entry points ---------------------------------------------------------
 bool g_cublas_init = false, g_engine_init = false;
 
-void init_cublas_handle() { (void)at::cuda::getCurrentCUDABlasHandle(); g_cublas_init = true; }
+void init_cublas_handle() {
+  at::globalContext().lazyInitDevice(c10::DeviceType::CUDA);  // the first CUDA use of the process may be this call
+  (void)at::cuda::getCurrentCUDABlasHandle();
+  g_cublas_init = true;
+}
 void destroy_cublas_handle() { g_cublas_init = false; }
 void init_engine() {
+  at::globalContext().lazyInitDevice(c10::DeviceType::CUDA);
   int sms = 0;
   check(b200_smoke_kernel(cur_stream(), &sms));
   g_engine_init = true;
@@ -448,6 +453,49 @@ struct PlanHandle {
                                   out.data_ptr<float>(), (uint32_t)flags, cur_stream()));
     return out;
   }
+  // ---- the FC layer in two calls (layers.cusparseLinear): everything between the Python autograd hooks happens here,
+  // so a launch-bound layer (config 2) pays two extension calls per step instead of ~20 Python-dispatched ops ----
+  // y[tokens, M] = act(x[tokens, K] * A^T + bias)
+  torch::Tensor fc_forward(const torch::Tensor& x, const c10::optional<torch::Tensor>& bias, bool relu, bool small) {
+    check_dense(x, "x");
+    const int64_t tokens = x.size(0);
+    const int64_t flags = relu ? B200_OP_RELU : 0;
+    if (small || would_use_tc(tokens, 0, flags)) {
+      auto y = torch::empty({tokens, M}, x.options());
+      forward(x, y, bias, flags | B200_OP_B_TRANSPOSED | B200_OP_C_TRANSPOSED);
+      return y;
+    }
+    auto yT = torch::empty({M, tokens}, x.options());
+    forward(x.t().contiguous(), yT, bias, flags);
+    return yT.t().contiguous();
+  }
+  // (d_values, d_x, d_bias) for g = dL/dy [tokens, M]; y is the saved output when the ReLU was fused
+  std::vector<c10::optional<torch::Tensor>> fc_backward(torch::Tensor g, const torch::Tensor& x,
+                                                        const c10::optional<torch::Tensor>& y, bool relu, bool small,
+                                                        bool need_values, bool need_x, bool need_bias) {
+    if (relu) g = g * (y.value() > 0);
+    g = g.contiguous();
+    check_dense(g, "grad_output");
+    const int64_t tokens = g.size(0);
+    std::vector<c10::optional<torch::Tensor>> out(3);
+    if (need_values) {
+      if (small || would_use_tc(tokens, 2, 0)) out[0] = backward_A(g, x, B200_OP_B_TRANSPOSED);
+      else out[0] = backward_A(g.t().contiguous(), x.t().contiguous(), 0);
+    }
+    if (need_x) {
+      if (small || would_use_tc(tokens, 1, 0)) {
+        auto dx = torch::empty({tokens, K}, g.options());
+        backward_B(g, dx, B200_OP_B_TRANSPOSED | B200_OP_C_TRANSPOSED);
+        out[1] = dx;
+      } else {
+        auto dxT = torch::empty({K, tokens}, g.options());
+        backward_B(g.t().contiguous(), dxT, 0);
+        out[1] = dxT.t().contiguous();
+      }
+    }
+    if (need_bias) out[2] = g.sum(0);
+    return out;
+  }
   void values_updated() { check(b200_plan_values_updated(plan)); }
   bool would_use_tc(int64_t N, int64_t side, int64_t flags) {
     return b200_plan_would_use_tc(plan, (int)side, N, (uint32_t)flags) != 0;
@@ -506,6 +554,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("flags") = 0)
       .def("backward_B", &PlanHandle::backward_B, py::arg("G"), py::arg("dB"), py::arg("flags") = 0)
       .def("backward_A", &PlanHandle::backward_A, py::arg("G"), py::arg("B"), py::arg("flags") = 0)
+      .def("fc_forward", &PlanHandle::fc_forward, py::arg("x"), py::arg("bias") = py::none(), py::arg("relu") = false,
+           py::arg("small") = false)
+      .def("fc_backward", &PlanHandle::fc_backward)
       .def("values_updated", &PlanHandle::values_updated)
       .def("would_use_tc", &PlanHandle::would_use_tc, py::arg("N"), py::arg("side") = 0, py::arg("flags") = 0)
       .def("last_path", &PlanHandle::last_path);

@@ -768,7 +768,24 @@ spmm_strided_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col
   csr_order_spmm(row_ptr, col, val, M, N, B, b_sk, b_sn, C, c_sm, c_sn, bias, relu != 0);
 }
 
+__global__ void __launch_bounds__(256)
+sddmm_strided_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int N,
+                     const float* __restrict__ G, long long g_sm, long long g_sn, const float* __restrict__ B,
+                     long long b_sk, long long b_sn, float* __restrict__ out) {
+  csr_order_sddmm(row_ptr, col, M, N, G, g_sm, g_sn, B, b_sk, b_sn, out);
+}
+
 }  // namespace
+
+// generic strided SDDMM (any G / B strides): small problems whose operands are held transposed
+int launch_sddmm_strided(const int* row_ptr, const int* col, int M, int N, const float* G, long long g_sm,
+                         long long g_sn, const float* B, long long b_sk, long long b_sn, float* out, cudaStream_t s) {
+  if (M == 0) return B200_OK;
+  const int blocks = (int)std::min<long long>(((long long)M + 7) / 8, (long long)device_sm_count() * 16);
+  sddmm_strided_kernel<<<blocks, 256, 0, s>>>(row_ptr, col, M, N, G, g_sm, g_sn, B, b_sk, b_sn, out);
+  B200_LAUNCH_OK("sddmm_strided_kernel");
+  return B200_OK;
+}
 
 int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, int M, int N, const float* B,
                         long long b_sk, long long b_sn, float* C, long long c_sm, long long c_sn,
