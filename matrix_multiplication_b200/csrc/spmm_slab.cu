@@ -20,7 +20,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SLAB_WARPS = 32;
-constexpr int SLAB_ROWS_MAX = 768;  // rows of C a CTA accumulates at a time (48 KB of sums at N = 16)
+constexpr int SLAB_ROWS_MAX = 1024;  // rows of C a CTA accumulates at a time (32 per warp; 64 KB of sums at N = 16)
 
 // slab_ptr[row * (S + 1) + s] = first non-zero of `row` whose column is >= s * rows_per_slab
 __global__ void slab_ptr_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M, int S,
@@ -91,64 +91,79 @@ spmm_slab_kernel(const int* __restrict__ col, const float* __restrict__ val, con
       if (tid == 0 && s + 1 < S) issue_slab(s + 1, b ^ 1);  // buffer b^1 was released by the barrier ending slab s-1
       if (b) { mbar_wait(full + 1, phase1); phase1 ^= 1u; } else { mbar_wait(full + 0, phase0); phase0 ^= 1u; }
       const float* slab = (b ? slab_buf1 : slab_buf0) - (size_t)s * rows_per_slab * N;  // indexed by the global column
-      // this warp's rows: c0 + warp, c0 + warp + 32, ...; their segment in slab s is [sp[s], sp[s+1])
-      int row = c0 + warp;
-      int q0 = 0, q1 = 0;
-      if (row < c1) {
-        q0 = __ldg(slab_ptr + (size_t)row * (S + 1) + s);
-        q1 = __ldg(slab_ptr + (size_t)row * (S + 1) + s + 1);
+      // this warp's rows: c0 + warp + 32 i (at most 32 of them); lane i fetches the bounds of row i's segment in this
+      // slab once, the loop below gets them by shuffle: no dependent global load between two batches
+      const int nvis = (c1 - c0 - warp + SLAB_WARPS - 1) / SLAB_WARPS;
+      int myq0 = 0, myq1 = 0;
+      if (lane < nvis) {
+        const size_t r = (size_t)(c0 + warp + SLAB_WARPS * lane);
+        myq0 = __ldg(slab_ptr + r * (S + 1) + s);
+        myq1 = __ldg(slab_ptr + r * (S + 1) + s + 1);
       }
-      while (row < c1) {
-        // prefetch the next row's segment bounds while this one is consumed
-        const int nrow = row + SLAB_WARPS;
-        int nq0 = 0, nq1 = 0;
-        if (nrow < c1) {
-          nq0 = __ldg(slab_ptr + (size_t)nrow * (S + 1) + s);
-          nq1 = __ldg(slab_ptr + (size_t)nrow * (S + 1) + s + 1);
+      // flat walk over the batches (64 non-zeros) of all segments, the next batch's loads in flight while the current
+      // one is consumed
+      int vi = -1, base = 0, q1 = 0;
+      auto advance = [&](int& vi_, int& base_, int& q1_) -> bool {
+        base_ += 64;
+        while (base_ >= q1_) {
+          if (++vi_ >= nvis) return false;
+          base_ = __shfl_sync(FULL, myq0, vi_);
+          q1_ = __shfl_sync(FULL, myq1, vi_);
         }
-        if (q1 > q0) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int base = q0; base < q1; base += 64) {  // two coalesced batches of 32 non-zeros in flight
-            int cc[2];
-            float aa[2];
+        return true;
+      };
+      auto load = [&](int base_, int q1_, int (&cc)[2], float (&aa)[2]) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int q = base + u * 32 + lane;
-              cc[u] = (q < q1) ? __ldcs(col + q) : -1;
-              aa[u] = (q < q1) ? __ldcs(val + q) : 0.f;
-            }
+        for (int u = 0; u < 2; ++u) {
+          const int q = base_ + u * 32 + lane;
+          cc[u] = (q < q1_) ? __ldcs(col + q) : -1;
+          aa[u] = (q < q1_) ? __ldcs(val + q) : 0.f;
+        }
+      };
+      int cc[2], ncc[2];
+      float aa[2], naa[2];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      bool have = advance(vi, base, q1);
+      if (have) load(base, q1, cc, aa);
+      while (have) {
+        int nvi = vi, nbase = base, nq1 = q1;
+        const bool nhave = advance(nvi, nbase, nq1);
+        if (nhave) load(nbase, nq1, ncc, naa);
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (base + u * 32 < q1) {
+        for (int u = 0; u < 2; ++u) {
+          if (base + u * 32 < q1) {
 #pragma unroll
-                for (int sub = 0; sub < LPR; ++sub) {  // group g takes non-zero sub * G + g of the batch
-                  const int cj = __shfl_sync(FULL, cc[u], sub * G + g);
-                  const float aj = __shfl_sync(FULL, aa[u], sub * G + g);
-                  if (cj >= 0) {
-                    const float4 bv = *reinterpret_cast<const float4*>(slab + (size_t)cj * N + 4 * l);
-                    acc[0] = fmaf(aj, bv.x, acc[0]);
-                    acc[1] = fmaf(aj, bv.y, acc[1]);
-                    acc[2] = fmaf(aj, bv.z, acc[2]);
-                    acc[3] = fmaf(aj, bv.w, acc[3]);
-                  }
-                }
+            for (int sub = 0; sub < LPR; ++sub) {  // group g takes non-zero sub * G + g of the batch
+              const int cj = __shfl_sync(FULL, cc[u], sub * G + g);
+              const float aj = __shfl_sync(FULL, aa[u], sub * G + g);
+              if (cj >= 0) {
+                const float4 bv = *reinterpret_cast<const float4*>(slab + (size_t)cj * N + 4 * l);
+                acc[0] = fmaf(aj, bv.x, acc[0]);
+                acc[1] = fmaf(aj, bv.y, acc[1]);
+                acc[2] = fmaf(aj, bv.z, acc[2]);
+                acc[3] = fmaf(aj, bv.w, acc[3]);
               }
             }
           }
-          // combine the G groups (fixed tree: deterministic), group 0 adds into the row's running sum
+        }
+        if (base + 64 >= q1) {
+          // last batch of the segment: combine the G groups (fixed tree: deterministic), group 0 adds into the row's sum
 #pragma unroll
           for (int o = 16; o >= LPR; o >>= 1) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(FULL, acc[v], o);
           }
           if (g == 0) {
-            float4* dst = reinterpret_cast<float4*>(s_acc + (size_t)(row - c0) * N + 4 * l);
+            float4* dst = reinterpret_cast<float4*>(s_acc + (size_t)(warp + SLAB_WARPS * vi) * N + 4 * l);
             float4 t = *dst;
             t.x += acc[0]; t.y += acc[1]; t.z += acc[2]; t.w += acc[3];
             *dst = t;
           }
+          acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         }
-        row = nrow; q0 = nq0; q1 = nq1;
+        vi = nvi; base = nbase; q1 = nq1; have = nhave;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { cc[u] = ncc[u]; aa[u] = naa[u]; }
       }
       __syncthreads();  // slab s consumed by every warp: its buffer may be refilled
     }
@@ -186,7 +201,10 @@ bool slab_wanted(int M, int K, long long nnz, int N, const float* B, long long l
   const int rps = slab_rows_per_slab(N);
   const long long S = ((long long)K + rps - 1) / rps;
   if (S > 16 || nnz < (1LL << 20) || M <= 0) return false;
-  return nnz >= 6LL * M * S;  // at least ~6 non-zeros per (row, slab) visit
+  // at least ~48 non-zeros per (row, slab) visit: below that the per-visit bookkeeping (segment bounds, group
+  // reduction, running-sum update) outweighs the cheaper gathers (measured: 16384^2 @99 % x 16, 12 per visit, is
+  // 2x slower here than on the lane-group kernel; @90 %, 126 per visit, 1.3x faster; profiles/r2_ncu_fwd_n16.md)
+  return nnz >= 48LL * M * S;
 }
 
 void slab_store_free(SlabStore* st) {

@@ -39,6 +39,9 @@ for _ in range(3):
     elif what == "c3_sddmm_tc":
         plan.backward_A_ex(G, B, dv, flags=OP_FORCE_TC)
     elif what == "c5_n16_gather":
+        capi.set_option("slab_mode", 0)
+        plan.forward_ex(B, C, flags=OP_NO_TC)
+    elif what == "c5_n16_slab":
         plan.forward_ex(B, C, flags=OP_NO_TC)
     elif what == "c4_sddmm":
         plan.backward_A_ex(G, B, dv, flags=OP_NO_TC)
