@@ -309,15 +309,18 @@ int b200_set_option(const char* name, int64_t value) {
     B200_REQUIRE(value == 0 || (value % 64 == 0 && value >= 64 && value <= 256), "tc_nt must be 0 or a multiple of 64 up to 256");
     options().tc_nt = (int)value; return B200_OK;
   }
-  if (!strcmp(name, "tc_terms")) { options().tc_terms = (int)value & 7; return B200_OK; }
+  if (!strcmp(name, "tc_terms")) { options().tc_terms = (int)value & 63;  /* bits 3-5: timing studies (skip store / B copy / A copy) */ return B200_OK; }
   if (!strcmp(name, "tc_chunk")) { options().tc_chunk = (int)std::max<int64_t>(1, value); return B200_OK; }
   if (!strcmp(name, "tc_kind")) { options().tc_kind = value ? 1 : 0; return B200_OK; }
+  if (!strcmp(name, "tc_pair")) { options().tc_pair = value ? 1 : 0; return B200_OK; }
   if (!strcmp(name, "tc_min_density_pct")) { options().tc_min_density_pct = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
   return B200_ERR_INVALID;
 }
 int64_t b200_get_option(const char* name) {
   if (!name) return -1;
+  if (!strcmp(name, "tc_last_kernel")) return b200::g_tc_last_kernel;
+  if (!strcmp(name, "tc_pair_capacity")) return b200::g_tc_pair_capacity;
   if (!strcmp(name, "stage_mode")) return options().stage_mode;
   if (!strcmp(name, "items_per_task")) return options().items_per_task;
   if (!strcmp(name, "pipeline")) return options().pipeline;
@@ -332,6 +335,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "tc_terms")) return options().tc_terms;
   if (!strcmp(name, "tc_chunk")) return options().tc_chunk;
   if (!strcmp(name, "tc_kind")) return options().tc_kind;
+  if (!strcmp(name, "tc_pair")) return options().tc_pair;
   if (!strcmp(name, "tc_min_density_pct")) return options().tc_min_density_pct;
   return -1;
 }

@@ -61,7 +61,8 @@ struct Options {
   int tc_mode = 1;         // 0 = never, 1 = auto (density / N rule), 2 = whenever the shape allows it
   int tc_nt = 0;           // tile width override (multiple of 32, <= 256); 0 = auto
   int tc_terms = 7;        // which split-precision products are issued: 1 hi*hi, 2 hi*lo, 4 lo*hi
-  int tc_chunk = 4;        // k-tiles accumulated in TMEM between two fp32 register accumulations
+  int tc_chunk = 8;        // k-tiles accumulated in TMEM between two fp32 register accumulations (<= 96 truncating adds)
+  int tc_pair = 0;         // 1 = CTA pairs (cta_group::2: tc_spmm2_kernel), 0 = one CTA per tile (default: measured equal, profiles/r2_tc_breakdown.md)
   int tc_kind = 1;         // 0 = tf32 hi/lo split, 1 = fp16 hi/lo split with row / column scaling (default)
   int tc_min_density_pct = 2;  // auto rule: never below this density (percent of M*K); above it a cost model decides
 };
@@ -315,6 +316,11 @@ struct TcStore {
   int M = 0, K = 0, MB = 0, KT = 0, n_tiles = 0;
   int kind = 0;                   // element kind of the split (0 tf32, 1 fp16)
   float* row_scale = nullptr;     // [M] fp16 kind: factor that undoes the per-row scaling of A
+  // CTA-pair kernel: per pair of 128-row blocks the union of stored k-tiles + each block's slot (n_tiles = zero tile)
+  int MB2 = 0, n_pair_tiles = 0;
+  int* pair_ptr = nullptr;
+  int* pair_kt = nullptr;
+  int* pair_slot = nullptr;
   int* blk_ptr = nullptr;         // [MB + 1] first stored tile of every 128-row block
   int* blk_kt = nullptr;          // [n_tiles] k-tile index of every stored tile
   int* scan = nullptr;            // [MB * KT] slot of tile (mb, kt) (exclusive scan of the occupancy flags)
@@ -341,6 +347,7 @@ int slab_store_build(const int* row_ptr, const int* col, int M, int K, int nnz, 
 void slab_store_free(SlabStore* st);
 int launch_spmm_slab(const SlabStore& st, const int* col, const float* val, const float* B, float* C, long long ldc,
                      const float* bias, int relu, cudaStream_t s);
+extern int g_tc_last_kernel, g_tc_pair_capacity;  // diagnostics of the last tensor-core launch (tc_gemm.cu)
 // pattern of a CSR matrix for the tensor-core SDDMM's sampling epilogue
 struct TcSample {
   int M = 0, K = 0, groups = 0;

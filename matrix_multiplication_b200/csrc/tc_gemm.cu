@@ -106,6 +106,34 @@ __global__ void tc_list_tiles_kernel(const int* __restrict__ flags, const int* _
   if (i == n - 1) blk_ptr[MB] = scan[i] + flags[i];
 }
 
+// CTA-pair lists: per pair of 128-row blocks the union of their stored k-tiles and each block's tile slot
+__global__ void tc_pair_flags_kernel(const int* __restrict__ flags, int MB, int MB2, int KT, int* __restrict__ pflags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)MB2 * KT) return;
+  const int mp = (int)(i / KT), kt = (int)(i % KT);
+  int f = flags[(size_t)(2 * mp) * KT + kt];
+  if (2 * mp + 1 < MB) f |= flags[(size_t)(2 * mp + 1) * KT + kt];
+  pflags[i] = f;
+}
+__global__ void tc_pair_list_kernel(const int* __restrict__ flags, const int* __restrict__ scan,
+                                    const int* __restrict__ pflags, const int* __restrict__ pscan, int MB, int MB2, int KT,
+                                    int zero_slot, int n_pair_tiles, int* __restrict__ pair_ptr, int* __restrict__ pair_kt,
+                                    int* __restrict__ pair_slot) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)MB2 * KT;
+  if (i >= n) return;
+  const int mp = (int)(i / KT), kt = (int)(i % KT);
+  if (kt == 0) pair_ptr[mp] = pscan[i];
+  if (i == n - 1) pair_ptr[MB2] = pscan[i] + pflags[i];
+  if (pflags[i]) {
+    const int idx = pscan[i];
+    pair_kt[idx] = kt;
+    const size_t c0 = (size_t)(2 * mp) * KT + kt, c1 = (size_t)(2 * mp + 1) * KT + kt;
+    pair_slot[idx] = flags[c0] ? scan[c0] : zero_slot;
+    pair_slot[(size_t)n_pair_tiles + idx] = (2 * mp + 1 < MB && flags[c1]) ? scan[c1] : zero_slot;
+  }
+}
+
 template <int KIND>
 __global__ void tc_pack_a_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col,
                                  const float* __restrict__ val, int M, int KT, const int* __restrict__ scan,
@@ -477,6 +505,13 @@ struct TcParams {
   int groups;
   const float* G;             // raw G for the CSR-order pass
   long long g_sm, g_sn;
+  // CTA-pair kernel (cta_group::2): 128-row blocks 2 mp and 2 mp + 1 share every B tile; per pair the union of their
+  // stored k-tiles, and for each of the two blocks the tile slot (the all-zero tile when that block has none there)
+  const int* pair_ptr;        // [MB2 + 1]
+  const int* pair_kt;         // [n_pair_tiles]
+  const int* pair_slot;       // [2][n_pair_tiles]
+  int n_pair_tiles, MB2;
+  int pair_ptr_ok;            // the pair lists (or the padded SDDMM operand) are in place
 };
 
 // exit protocol: the last CTA to leave re-arms the non-finite flag and the ticket for the next launch
@@ -530,6 +565,77 @@ __device__ __forceinline__ void csr_order_sddmm(const int* __restrict__ row_ptr,
 #pragma unroll
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) out[p] = acc;
+    }
+  }
+}
+
+// Final step of a tile for one epilogue thread: acc[] holds this thread's row (m) x 128-column share of the tile.
+// SpMM: scale, + bias, ReLU, store C (or C^T); SDDMM: write the entries that lie on A's pattern.
+template <int KIND, bool SDDMM>
+__device__ __forceinline__ void tc_tile_store(const TcParams& p, const float (&acc)[128], int mb, int nb, int q, int half,
+                                          int ntw, int lane) {
+  const bool relu = (p.flags & 4u) != 0, ct = (p.flags & 2u) != 0;
+  const bool vec4 = !ct && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  const int m = mb * BM + q * 32 + lane;
+  if constexpr (SDDMM) {
+    // sample the tile on A's pattern: bit j of the mask <=> (m, 32 g + j) is a non-zero; its position in the CSR
+    // value array is the group's offset plus the number of set bits below j
+    float rs = 1.f;
+    if constexpr (KIND == KIND_F16) rs = (m < p.M) ? scale_down(scale_exp(__ldg(p.amax + m))) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k0 = nb * p.Nt + half * ntw + c * 32;
+      const int grp = k0 >> 5;
+      if (c * 32 < ntw && grp < p.groups && m < p.M) {
+        const uint32_t mask = __ldg(p.samp_mask + (size_t)grp * p.M + m);
+        const int base = __ldg(p.samp_off + (size_t)grp * p.M + m);
+        if (mask != 0u) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if ((mask >> j) & 1u) {
+              float x = acc[c * 32 + j];
+              if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp(__ldg(p.colmax + k0 + j)));
+              p.C[base + __popc(mask & ((1u << j) - 1u))] = x;
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+  const float bias = (p.bias != nullptr && m < p.M) ? __ldg(p.bias + m) : 0.f;
+  float rs = 1.f;
+  if constexpr (KIND == KIND_F16) rs = (m < p.M) ? __ldg(p.row_scale + m) : 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int n0 = nb * p.Nt + half * ntw + c * 32;
+    if (c * 32 < ntw && n0 < p.N) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = acc[c * 32 + j];
+        if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp((n0 + j < p.N) ? __ldg(p.colmax + n0 + j) : 0u));
+        x += bias;
+        v[j] = relu ? fmaxf(x, 0.f) : x;
+      }
+      if (ct) {  // C^T [N, M]: a register is one n, the 32 lanes are 32 consecutive m -> coalesced
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) p.C[(long long)(n0 + j) * p.ldc + m] = v[j];
+        }
+      } else if (m < p.M) {
+        float* dst = p.C + (long long)m * p.ldc + n0;
+        if (vec4 && n0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            __stcs(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) dst[j] = v[j];
+        }
+      }
     }
   }
 }
@@ -599,12 +705,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
           if (!ok) break;
           const int kt = SDDMM ? t : __ldg(p.blk_kt + t);
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(full + stage, (uint32_t)stage_bytes);
+          const bool cp_a = !(p.terms & 32), cp_b = !(p.terms & 16);  // (timing studies: skip a copy)
+          const uint32_t tx = (cp_a ? (uint32_t)A_TILE : 0u) + (cp_b ? (uint32_t)p.Nt * 256u : 0u);
+          if (tx) mbar_expect_tx(full + stage, tx); else mbar_arrive(full + stage);
           const unsigned char* a_src = SDDMM ? p.a_tiles + ((size_t)kt * p.NGa + (size_t)mb * (BM / 8)) * ATOM
                                              : p.a_tiles + (size_t)t * A_TILE;
-          tma_bulk_g2s(sa, a_src, A_TILE, full + stage);
-          tma_bulk_g2s(sa + A_TILE, p.b_pack + ((size_t)kt * p.NG + (size_t)nb * (p.Nt / 8)) * ATOM,
-                       (uint32_t)p.Nt * 256u, full + stage);
+          if (cp_a) tma_bulk_g2s(sa, a_src, A_TILE, full + stage);
+          if (cp_b)
+            tma_bulk_g2s(sa + A_TILE, p.b_pack + ((size_t)kt * p.NG + (size_t)nb * (p.Nt / 8)) * ATOM,
+                         (uint32_t)p.Nt * 256u, full + stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -654,8 +763,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
     const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
     const int ntw = p.Nt >> 1;            // columns per warp (multiple of 32, <= 128)
-    const bool relu = (p.flags & 4u) != 0, ct = (p.flags & 2u) != 0;
-    const bool vec4 = !ct && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     uint32_t g = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
@@ -685,68 +792,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
         if (lane == 0) mbar_arrive(acc_empty + as);  // this warp's part of the buffer is drained
       }
       if (!ok) break;
-      const int m = mb * BM + q * 32 + lane;
-      if constexpr (SDDMM) {
-        // sample the tile on A's pattern: bit j of the mask <=> (m, 32 g + j) is a non-zero; its position in the CSR
-        // value array is the group's offset plus the number of set bits below j
-        float rs = 1.f;
-        if constexpr (KIND == KIND_F16) rs = (m < p.M) ? scale_down(scale_exp(__ldg(p.amax + m))) : 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k0 = nb * p.Nt + half * ntw + c * 32;
-          const int grp = k0 >> 5;
-          if (c * 32 < ntw && grp < p.groups && m < p.M) {
-            const uint32_t mask = __ldg(p.samp_mask + (size_t)grp * p.M + m);
-            const int base = __ldg(p.samp_off + (size_t)grp * p.M + m);
-            if (mask != 0u) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if ((mask >> j) & 1u) {
-                  float x = acc[c * 32 + j];
-                  if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp(__ldg(p.colmax + k0 + j)));
-                  p.C[base + __popc(mask & ((1u << j) - 1u))] = x;
-                }
-              }
-            }
-          }
-        }
-        continue;
-      }
-      const float bias = (p.bias != nullptr && m < p.M) ? __ldg(p.bias + m) : 0.f;
-      float rs = 1.f;
-      if constexpr (KIND == KIND_F16) rs = (m < p.M) ? __ldg(p.row_scale + m) : 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int n0 = nb * p.Nt + half * ntw + c * 32;
-        if (c * 32 < ntw && n0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = acc[c * 32 + j];
-            if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp((n0 + j < p.N) ? __ldg(p.colmax + n0 + j) : 0u));
-            x += bias;
-            v[j] = relu ? fmaxf(x, 0.f) : x;
-          }
-          if (ct) {  // C^T [N, M]: a register is one n, the 32 lanes are 32 consecutive m -> coalesced
-            if (m < p.M) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) p.C[(long long)(n0 + j) * p.ldc + m] = v[j];
-            }
-          } else if (m < p.M) {
-            float* dst = p.C + (long long)m * p.ldc + n0;
-            if (vec4 && n0 + 32 <= p.N) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                __stcs(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) dst[j] = v[j];
-            }
-          }
-        }
-      }
+      if (!(p.terms & 8)) tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane);
     }
   }
   tc_fence_before();
@@ -754,6 +800,272 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  tc_exit_ticket(p.ctl);
+}
+
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2 ------------------------------------------------------------------
+// Two CTAs of a cluster (one TPC) multiply a 256 x Nt tile together: each holds its own 128 rows of A and HALF of
+// the B tile (Nt / 2 columns), the tensor cores of both SMs read both halves, each SM's TMEM receives its 128 rows of
+// the result.  Per stage and CTA: A 32 KB + B Nt * 128 B (64 KB at Nt = 256) instead of 96 KB: one third fewer bytes
+// through each SM's L2 port (the limiter of the single-CTA kernel, profiles/r2_ncu_tc.md) and 3 stages instead of 2.
+// Protocol (all mbarriers live at the same offsets in both CTAs; rank 0 = leader issues every MMA):
+//   full[s]      leader: own TMA bytes + one arrive relayed by the peer (its warp 1 waits for the peer's own full[s],
+//                then arrives remotely); peer: own TMA bytes
+//   empty[s]     released in BOTH CTAs by the leader's tcgen05.commit ... multicast::cluster
+//   acc_full[b]  published in both CTAs the same way; acc_empty[b] lives on the leader and collects the 16 epilogue
+//                warps of both CTAs (remote arrives)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// bounded wait with cluster-scope acquire (the barrier may be completed by the other CTA)
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* dbg, int code) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if ((it & 1023u) == 1023u) {
+      if (*reinterpret_cast<volatile int*>(dbg) != 0) return false;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        atomicCAS(dbg, 0, code);
+        return false;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                      uint32_t accumulate) {
+  if constexpr (KIND == KIND_F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+template <int KIND, bool SDDMM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_spmm2_kernel(const TcParams p) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  if (*reinterpret_cast<const volatile int*>(p.ctl) != 0) {  // Inf / NaN in a dense operand (uniform over the grid)
+    if constexpr (SDDMM) {
+      csr_order_sddmm(p.row_ptr, p.col, p.M, p.N, p.G, p.g_sm, p.g_sn, p.B, p.b_sk, p.b_sn, p.C);
+    } else {
+      const bool ctr = (p.flags & 2u) != 0;
+      csr_order_spmm(p.row_ptr, p.col, p.val, p.M, p.N, p.B, p.b_sk, p.b_sn, p.C, ctr ? 1 : p.ldc, ctr ? p.ldc : 1,
+                     p.bias, (p.flags & 4u) != 0);
+    }
+    tc_exit_ticket(p.ctl);
+    return;
+  }
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  unsigned char* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int b_bytes = p.Nt * 128;                 // this CTA's half of the B tile (Nt / 2 rows, hi + lo)
+  const int stage_bytes = A_TILE + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* acc_full = empty + MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full + i, rank == 0 ? 2 : 1);
+      mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, 2 * EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int n_tiles = p.MB2 * p.NB;
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A tile + own half of the B tile =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
+        const int mp = tile / p.NB, nb = tile % p.NB;
+        const int mb = 2 * mp + (int)rank;
+        const int t0 = SDDMM ? 0 : __ldg(p.pair_ptr + mp), t1 = SDDMM ? p.KT : __ldg(p.pair_ptr + mp + 1);
+        for (int t = t0; t < t1; ++t) {
+          ok = mbar_wait_cluster(empty + stage, phase ^ 1u, p.ctl + 1, 100 + stage);
+          if (!ok) break;
+          const int kt = SDDMM ? t : __ldg(p.pair_kt + t);
+          unsigned char* sa = smem + (size_t)stage * stage_bytes;
+          const bool cp_a = !(p.terms & 32), cp_b = !(p.terms & 16);  // (timing studies: skip a copy)
+          const uint32_t tx = (cp_a ? (uint32_t)A_TILE : 0u) + (cp_b ? (uint32_t)b_bytes : 0u);
+          if (tx) mbar_expect_tx(full + stage, tx); else mbar_arrive(full + stage);
+          const unsigned char* a_src =
+              SDDMM ? p.a_tiles + ((size_t)kt * p.NGa + (size_t)mb * (BM / 8)) * ATOM
+                    : p.a_tiles + (size_t)__ldg(p.pair_slot + (size_t)rank * p.n_pair_tiles + t) * A_TILE;
+          if (cp_a) tma_bulk_g2s(sa, a_src, A_TILE, full + stage);
+          if (cp_b)
+            tma_bulk_g2s(sa + A_TILE,
+                         p.b_pack + ((size_t)kt * p.NG + (size_t)nb * (p.Nt / 8) + (size_t)rank * (p.Nt / 16)) * ATOM,
+                         (uint32_t)b_bytes, full + stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 1) {
+      // ===== relay (peer CTA): my operands of a stage have landed -> tell the leader's full barrier =====
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
+        const int mp = tile / p.NB;
+        const int t0 = SDDMM ? 0 : __ldg(p.pair_ptr + mp), t1 = SDDMM ? p.KT : __ldg(p.pair_ptr + mp + 1);
+        for (int t = t0; t < t1; ++t) {
+          ok = mbar_wait_cluster(full + stage, phase, p.ctl + 1, 500 + stage);
+          if (!ok) break;
+          mbar_arrive_remote(full + stage, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
+      // ===== MMA issuer (leader CTA): one lane issues every tcgen05.mma of the pair =====
+      const uint32_t idesc = (1u << 4) | ((KIND == KIND_F16 ? 0u : 2u) << 7) | ((KIND == KIND_F16 ? 0u : 2u) << 10) |
+                             ((uint32_t)(p.Nt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t g = 0;
+      bool ok = true;
+      for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
+        const int mp = tile / p.NB;
+        const int t0 = SDDMM ? 0 : __ldg(p.pair_ptr + mp), t1 = SDDMM ? p.KT : __ldg(p.pair_ptr + mp + 1);
+        for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
+          const int as = (int)(g & 1u);
+          ok = mbar_wait_cluster(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(as * p.Nt);
+          uint32_t acc = 0;
+          const int c1 = min(c0 + p.chunk, t1);
+          for (int t = c0; t < c1; ++t) {
+            ok = mbar_wait_cluster(full + stage, phase, p.ctl + 1, 300 + stage);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + A_TILE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
+              const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
+              if (p.terms & 2) { umma2<KIND>(d, a_hi, b_lo, idesc, acc); acc = 1; }
+              if (p.terms & 4) { umma2<KIND>(d, a_lo, b_hi, idesc, acc); acc = 1; }
+              if (p.terms & 1) { umma2<KIND>(d, a_hi, b_hi, idesc, acc); acc = 1; }
+            }
+            umma_commit2(empty + stage);  // frees the slot in both CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit2(acc_full + as);  // both CTAs' epilogue warps
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): own 128 rows of the pair's tile =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ntw = p.Nt >> 1;
+    uint32_t g = 0;
+    bool ok = true;
+    for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
+      const int mp = tile / p.NB, nb = tile % p.NB;
+      const int mb = 2 * mp + (int)rank;
+      const int t0 = SDDMM ? 0 : __ldg(p.pair_ptr + mp), t1 = SDDMM ? p.KT : __ldg(p.pair_ptr + mp + 1);
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
+        const int as = (int)(g & 1u);
+        ok = mbar_wait_cluster(acc_full + as, (g >> 1) & 1u, p.ctl + 1, 400 + as);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.Nt + half * ntw);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < ntw) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(acc_empty + as, 0);  // the leader's barrier collects both CTAs
+      }
+      if (!ok) break;
+      if (mb < p.MB && !(p.terms & 8)) tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the other CTA may still signal it or read its smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
   tc_exit_ticket(p.ctl);
 }
@@ -803,6 +1115,7 @@ int launch_spmm_strided(const int* row_ptr, const int* col, const float* val, in
 
 void tc_store_free(TcStore* st) {
   cudaFree(st->blk_ptr); cudaFree(st->blk_kt); cudaFree(st->scan); cudaFree(st->tiles); cudaFree(st->row_scale);
+  cudaFree(st->pair_ptr); cudaFree(st->pair_kt); cudaFree(st->pair_slot);
   *st = TcStore{};
 }
 
@@ -856,7 +1169,7 @@ int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, 
   tc_list_tiles_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(flags, st->scan, st->MB, st->KT, st->blk_ptr,
                                                                        st->blk_kt);
   B200_LAUNCH_OK("tc_list_tiles_kernel");
-  const size_t bytes = std::max<size_t>((size_t)st->n_tiles, 1) * A_TILE;
+  const size_t bytes = ((size_t)st->n_tiles + 1) * A_TILE;  // + one all-zero tile (slot n_tiles) for the CTA-pair kernel
   if (cudaMalloc(&st->tiles, bytes) != cudaSuccess) {
     cudaGetLastError();
     set_error("cudaMalloc of %zu bytes for the block-dense tiles failed", bytes);
@@ -868,6 +1181,32 @@ int tc_store_build(const int* row_ptr, const int* col, const float* val, int M, 
   B200_CUDA_OK(cudaMemsetAsync(st->tiles, 0, bytes, s));
   int rc = tc_launch_pack_a(row_ptr, col, val, nnz, st, s);
   if (rc) return rc;
+  {  // lists for the CTA-pair kernel
+    st->MB2 = (st->MB + 1) / 2;
+    const size_t pcells = (size_t)st->MB2 * st->KT;
+    int *pflags = nullptr, *pscan = nullptr;
+    B200_CUDA_OK(cudaMalloc(&pflags, pcells * sizeof(int)));
+    B200_CUDA_OK(cudaMalloc(&pscan, pcells * sizeof(int)));
+    B200_CUDA_OK(cudaMalloc(&st->pair_ptr, ((size_t)st->MB2 + 1) * sizeof(int)));
+    tc_pair_flags_kernel<<<(unsigned)((pcells + 255) / 256), 256, 0, s>>>(flags, st->MB, st->MB2, st->KT, pflags);
+    B200_LAUNCH_OK("tc_pair_flags_kernel");
+    B200_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pflags, pscan, (int)pcells, s));  // pcells <= cells
+    int plast[2] = {0, 0};
+    B200_CUDA_OK(cudaMemcpyAsync(&plast[0], pscan + pcells - 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(&plast[1], pflags + pcells - 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    st->n_pair_tiles = plast[0] + plast[1];
+    const size_t npt = std::max<size_t>((size_t)st->n_pair_tiles, 1);
+    B200_CUDA_OK(cudaMalloc(&st->pair_kt, npt * sizeof(int)));
+    B200_CUDA_OK(cudaMalloc(&st->pair_slot, 2 * npt * sizeof(int)));
+    tc_pair_list_kernel<<<(unsigned)((pcells + 255) / 256), 256, 0, s>>>(flags, st->scan, pflags, pscan, st->MB, st->MB2,
+                                                                        st->KT, st->n_tiles, (int)npt, st->pair_ptr,
+                                                                        st->pair_kt, st->pair_slot);
+    B200_LAUNCH_OK("tc_pair_list_kernel");
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(pflags);
+    cudaFree(pscan);
+  }
   B200_CUDA_OK(cudaStreamSynchronize(s));
   cudaFree(flags);
   cudaFree(tmp);
@@ -939,12 +1278,58 @@ static int tc_pack_operand(const float* X, long long ld, int rows, int depth, bo
   return B200_OK;
 }
 
+int g_tc_last_kernel = 0;    // 1 = one CTA per tile, 2 = CTA pairs (diagnostics: b200_get_option("tc_last_kernel"))
+int g_tc_pair_capacity = -1; // co-resident CTA pairs reported by the occupancy query
+
+// co-resident CTA pairs of the pair kernel on this device (0 = cluster launch not possible)
+template <int KIND, bool SDDMM>
+static int tc_pair_capacity(size_t smem) {
+  static int cached[64] = {0};
+  static bool known[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (!known[dev & 63]) {
+    int n = 0;
+    if (cudaFuncSetAttribute(tc_spmm2_kernel<KIND, SDDMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) ==
+        cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * 74, 1, 1);
+      cfg.blockDim = dim3(TC_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_spmm2_kernel<KIND, SDDMM>, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    cached[dev & 63] = n;
+    known[dev & 63] = true;
+  }
+  return cached[dev & 63];
+}
+
 template <int KIND, bool SDDMM>
 static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
-  const int stage_bytes = A_TILE + p.Nt * 256;
-  p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes));
   p.chunk = std::max(1, options().tc_chunk);
   p.terms = options().tc_terms;
+  // CTA pairs (cta_group::2) when there are at least two row blocks: each CTA stages A + half of the B tile
+  if (options().tc_pair != 0 && p.MB >= 2 && p.pair_ptr_ok) {
+    const int stage2 = A_TILE + p.Nt * 128;
+    p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage2));
+    const size_t smem2 = (size_t)p.stages * stage2 + 1024 + 256;
+    const int cap = tc_pair_capacity<KIND, SDDMM>(smem2);
+    g_tc_pair_capacity = cap;
+    if (cap > 0) {
+      g_tc_last_kernel = 2;
+      const int pairs = std::max(1, std::min(cap, p.MB2 * p.NB));
+      tc_spmm2_kernel<KIND, SDDMM><<<2 * pairs, TC_THREADS, smem2, s>>>(p);
+      B200_LAUNCH_OK(SDDMM ? "tc_sddmm2_kernel" : "tc_spmm2_kernel");
+      return B200_OK;
+    }
+  }
+  const int stage_bytes = A_TILE + p.Nt * 256;
+  p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes));
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -955,6 +1340,7 @@ static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
     attr_set[dev & 63] = true;
   }
   const int grid = std::max(1, std::min(device_sm_count(), tiles));
+  g_tc_last_kernel = 1;
   tc_spmm_kernel<KIND, SDDMM><<<grid, TC_THREADS, smem, s>>>(p);
   B200_LAUNCH_OK(SDDMM ? "tc_sddmm_kernel" : "tc_spmm_kernel");
   return B200_OK;
@@ -977,6 +1363,8 @@ static int tc_launch(const TcStore& st, const int* row_ptr, const int* col, cons
   p.C = C; p.ldc = ldc; p.M = st.M; p.N = N; p.bias = bias; p.flags = flags;
   p.row_scale = st.row_scale; p.colmax = colmax;
   p.MB = st.MB; p.NB = NB; p.Nt = nt;
+  p.pair_ptr = st.pair_ptr; p.pair_kt = st.pair_kt; p.pair_slot = st.pair_slot;
+  p.n_pair_tiles = std::max(st.n_pair_tiles, 1); p.MB2 = st.MB2; p.pair_ptr_ok = st.pair_ptr != nullptr;
   p.ctl = ctl;
   p.row_ptr = row_ptr; p.col = col; p.val = val; p.B = B;
   p.b_sk = bt ? 1 : ldb; p.b_sn = bt ? ldb : 1;
@@ -1055,7 +1443,7 @@ int tc_sample_build(const int* row_ptr, const int* col, int M, int K, int nnz, T
 // workspace of the SDDMM: [control 256 B][row maxima of G][row maxima of B][packed G][packed B]
 size_t tc_sddmm_ws_bytes(int M, int K, int N, int nt, int kind) {
   const size_t KT = (size_t)(N + bk_of(kind) - 1) / bk_of(kind);
-  const size_t NGa = (size_t)((M + BM - 1) / BM) * (BM / 8);
+  const size_t NGa = (size_t)(((M + BM - 1) / BM + 1) / 2 * 2) * (BM / 8);  // an even number of 128-row blocks (CTA pairs)
   const size_t NGb = (size_t)((K + nt - 1) / nt) * (nt / 8);
   return 256 + tc_colmax_bytes((int)NGa * 8) + tc_colmax_bytes((int)NGb * 8) + KT * (NGa + NGb) * ATOM;
 }
@@ -1066,7 +1454,7 @@ static int tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, cons
                     cudaStream_t s) {
   const int M = sm.M, K = sm.K;
   const int KT = (N + bk_of(KIND) - 1) / bk_of(KIND);
-  const int MB = (M + BM - 1) / BM, NGa = MB * (BM / 8);
+  const int MB = (M + BM - 1) / BM, MB2 = (MB + 1) / 2, NGa = 2 * MB2 * (BM / 8);
   const int NB = (K + nt - 1) / nt, NGb = NB * (nt / 8);
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
   int* ctl = reinterpret_cast<int*>(base);
@@ -1087,6 +1475,7 @@ static int tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, cons
   p.amax = amax; p.colmax = bmax;
   p.samp_mask = sm.mask; p.samp_off = sm.off; p.groups = sm.groups;
   p.MB = MB; p.NB = NB; p.Nt = nt;
+  p.MB2 = MB2; p.pair_ptr_ok = 1;
   p.ctl = ctl;
   p.row_ptr = row_ptr; p.col = col;
   p.G = G; p.g_sm = transposed ? 1 : ldg; p.g_sn = transposed ? ldg : 1;

@@ -19,7 +19,7 @@ KINDS = [0, 1]  # 0: tf32 hi + lo, 1: fp16 hi + lo with row / column scaling
 @pytest.fixture(autouse=True)
 def _reset_options():
     yield
-    for k, v in (("tc_kind", capi.TC_KIND_DEFAULT), ("tc_nt", 0), ("tc_chunk", 4), ("tc_terms", 7), ("tc_mode", 1)):
+    for k, v in (("tc_kind", capi.TC_KIND_DEFAULT), ("tc_nt", 0), ("tc_chunk", 8), ("tc_terms", 7), ("tc_mode", 1)):
         capi.set_option(k, v)
 
 

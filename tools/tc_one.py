@@ -27,4 +27,5 @@ if len(sys.argv) > 7 and sys.argv[7] == "sddmm":
     for _ in range(iters):
         plan.backward_A_ex(G, B, dv, flags=OP_FORCE_TC)
     torch.cuda.synchronize()
+print("tc_last_kernel", capi.get_option("tc_last_kernel"), "pair capacity", capi.get_option("tc_pair_capacity"))
 print("rel_err", float((C.double() - ref).abs().max() / ref.abs().max()), "timeout", plan.tc_timeout())

@@ -97,7 +97,7 @@ def run_case(name, A, B, flags=OP_FORCE_TC, bias=None, opts=None, timing=False, 
     except Exception as e:  # noqa: BLE001
         rec["error"] = repr(e)
     for k in (opts or {}):
-        capi.set_option(k, {"tc_terms": 7, "tc_chunk": 4, "tc_nt": 0, "tc_mode": 1, "tc_kind": 1}.get(k, 0))
+        capi.set_option(k, {"tc_terms": 7, "tc_chunk": 8, "tc_nt": 0, "tc_mode": 1, "tc_kind": 1}.get(k, 0))
     plan.close()
     out(**rec)
     return rec
