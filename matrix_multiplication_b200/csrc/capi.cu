@@ -117,6 +117,9 @@ struct b200_plan {
   float* hB = nullptr; float* hC = nullptr; size_t hB_bytes = 0, hC_bytes = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t hev[2][16] = {};
+  // extra streams / events when a panel copy is split by rows over several copy engines (host_copy_split > 1)
+  std::vector<cudaStream_t> hx[2];
+  std::vector<cudaEvent_t> hxe[2];
   PeerSet* d_peers = nullptr;  // device copy of the peer pointers of the multi-GPU epilogue
   PeerSet h_peers{};           // what d_peers currently holds
   // block-dense tensor-core path: densified tiles of A (side 0) and A^T (side 1), built on first use
@@ -299,6 +302,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "slab_mode")) { options().slab_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "host_copy_mode")) { options().host_copy_mode = (int)value; return B200_OK; }
   if (!strcmp(name, "host_copy_ctas")) { options().host_copy_ctas = (int)value; return B200_OK; }
+  if (!strcmp(name, "host_copy_split")) { options().host_copy_split = (int)value; return B200_OK; }
   if (!strcmp(name, "tail_tasks")) { options().tail_tasks = (int)std::max<int64_t>(0, value); return B200_OK; }
   if (!strcmp(name, "d2c_warps")) {
     B200_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "d2c_warps must be 0, 2, 4, 8 or 16");
@@ -328,6 +332,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "slab_mode")) return options().slab_mode;
   if (!strcmp(name, "host_copy_mode")) return options().host_copy_mode;
   if (!strcmp(name, "host_copy_ctas")) return options().host_copy_ctas;
+  if (!strcmp(name, "host_copy_split")) return options().host_copy_split;
   if (!strcmp(name, "tail_tasks")) return options().tail_tasks;
   if (!strcmp(name, "d2c_warps")) return options().d2c_warps;
   if (!strcmp(name, "tc_mode")) return options().tc_mode;
@@ -571,6 +576,10 @@ int b200_plan_destroy(b200_plan* p) {
   slab_store_free(&p->slab[0]); slab_store_free(&p->slab[1]);
   tc_store_free(&p->tc[0]); tc_store_free(&p->tc[1]);
   for (int i = 0; i < 3; ++i) if (p->hs[i]) cudaStreamDestroy(p->hs[i]);
+  for (int d = 0; d < 2; ++d) {
+    for (auto st : p->hx[d]) cudaStreamDestroy(st);
+    for (auto ev : p->hxe[d]) cudaEventDestroy(ev);
+  }
   for (int j = 0; j < 2; ++j) for (int i = 0; i < 16; ++i) if (p->hev[j][i]) cudaEventDestroy(p->hev[j][i]);
   cudaGetLastError();
   delete p;
@@ -853,9 +862,40 @@ int b200_plan_forward_host(b200_plan* p, const float* h_B, int64_t N, float* h_C
   const bool sm_copy = options().host_copy_mode == 1 && panels > 1 && dB != nullptr && dC != nullptr && N % 4 == 0 &&
                        w % 4 == 0 && reinterpret_cast<uintptr_t>(dB) % 16 == 0 && reinterpret_cast<uintptr_t>(dC) % 16 == 0;
   const int copy_ctas = std::max(16, options().host_copy_ctas);
+  // a 2-D copy with short rows is limited by one copy engine, not by PCIe: split every panel copy by rows over
+  // `split` streams so that several engines work on it
+  const int split = (!sm_copy && panels > 1) ? std::max(1, std::min(8, options().host_copy_split)) : 1;
+  if (split > 1) {
+    for (int d = 0; d < 2; ++d) {
+      while ((int)p->hx[d].size() < split - 1) {
+        cudaStream_t st;
+        B200_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        p->hx[d].push_back(st);
+      }
+      while ((int)p->hxe[d].size() < (split - 1) * panels + panels) {
+        cudaEvent_t ev;
+        B200_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        p->hxe[d].push_back(ev);
+      }
+    }
+  }
   for (int i = 0; i < panels; ++i) {
     const size_t off = (size_t)i * w;
-    if (p->nnz > 0) {
+    if (p->nnz > 0 && split > 1) {
+      // rows [r0, r1) of the panel on stream c (c = 0: the main upload stream)
+      for (int c = 0; c < split; ++c) {
+        const size_t r0 = (size_t)p->K * c / split, r1 = (size_t)p->K * (c + 1) / split;
+        cudaStream_t st = c == 0 ? p->hs[0] : p->hx[0][c - 1];
+        if (r1 > r0)
+          B200_CUDA_OK(cudaMemcpy2DAsync(p->hB + r0 * N + off, pitch, h_B + r0 * N + off, pitch, (size_t)w * sizeof(float),
+                                         r1 - r0, cudaMemcpyHostToDevice, st));
+        if (c > 0) {
+          cudaEvent_t ev = p->hxe[0][(size_t)i * (split - 1) + (c - 1)];
+          B200_CUDA_OK(cudaEventRecord(ev, st));
+          B200_CUDA_OK(cudaStreamWaitEvent(p->hs[0], ev, 0));
+        }
+      }
+    } else if (p->nnz > 0) {
       if (sm_copy) {
         panel_copy_kernel<<<copy_ctas, 256, 0, p->hs[0]>>>(reinterpret_cast<float4*>(p->hB + off),
                                                           reinterpret_cast<const float4*>(dB + off), p->K, (int)(w / 4),
@@ -873,7 +913,21 @@ int b200_plan_forward_host(b200_plan* p, const float* h_B, int64_t N, float* h_C
     if (rc) return rc;
     B200_CUDA_OK(cudaEventRecord(p->hev[1][i], p->hs[1]));
     B200_CUDA_OK(cudaStreamWaitEvent(p->hs[2], p->hev[1][i], 0));
-    if (sm_copy) {
+    if (split > 1) {
+      for (int c = 0; c < split; ++c) {
+        const size_t r0 = (size_t)p->M * c / split, r1 = (size_t)p->M * (c + 1) / split;
+        cudaStream_t st = c == 0 ? p->hs[2] : p->hx[1][c - 1];
+        if (c > 0) B200_CUDA_OK(cudaStreamWaitEvent(st, p->hev[1][i], 0));
+        if (r1 > r0)
+          B200_CUDA_OK(cudaMemcpy2DAsync(h_C + r0 * N + off, pitch, p->hC + r0 * N + off, pitch, (size_t)w * sizeof(float),
+                                         r1 - r0, cudaMemcpyDeviceToHost, st));
+        if (c > 0) {
+          cudaEvent_t ev = p->hxe[1][(size_t)i * (split - 1) + (c - 1)];
+          B200_CUDA_OK(cudaEventRecord(ev, st));
+          B200_CUDA_OK(cudaStreamWaitEvent(p->hs[2], ev, 0));
+        }
+      }
+    } else if (sm_copy) {
       panel_copy_kernel<<<copy_ctas, 256, 0, p->hs[2]>>>(reinterpret_cast<float4*>(dC + off),
                                                         reinterpret_cast<const float4*>(p->hC + off), p->M, (int)(w / 4),
                                                         N / 4);

@@ -55,6 +55,7 @@ struct Options {
   int slab_mode = 1;       // narrow-N shared-memory slab kernel: 0 = never, 1 = when slab_wanted() says so
   int host_copy_mode = 0;  // b200_plan_forward_host panel copies: 0 = copy engine (cudaMemcpy2DAsync), 1 = SM copy kernel
   int host_copy_ctas = 32; // CTAs of one SM-driven panel copy
+  int host_copy_split = 1; // row chunks (= copy engines) per panel copy of the host pipeline
   int tail_tasks = 0;      // short tasks (W/4) at the end of a forward launch; measured no gain on config 4 and its shards (profiles/r2_scaling.md): off
   int d2c_warps = 0;       // dense->CSR one-pass tile size in warps (2, 4, 8, 16; 0 = default 4)
   // block-dense tensor-core path (tc_gemm.cu)

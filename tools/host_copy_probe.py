@@ -12,13 +12,12 @@ plan = capi.Plan(crow, col, val, (M, K))
 B = torch.rand(K, N).pin_memory()
 C = torch.empty(M, N).pin_memory()
 ref = None
-for mode, ctas in ((0, 32), (1, 16), (1, 32), (1, 64), (1, 148)):
-    for panels in (1, 2, 4, 8):
-        capi.set_option("host_copy_mode", mode); capi.set_option("host_copy_ctas", ctas)
+for split in (1, 2, 3, 4):
+    for panels in (2, 4, 8):
+        capi.set_option("host_copy_mode", 0); capi.set_option("host_copy_split", split)
         for _ in range(2): plan.forward_host(B, C, panels)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for _ in range(5): plan.forward_host(B, C, panels)
         torch.cuda.synchronize(); ms = (time.perf_counter() - t0) / 5 * 1e3
         if ref is None: ref = C.clone()
-        print(f"mode {mode} ctas {ctas:3d} panels {panels}: {ms:.3f} ms  same={bool(torch.equal(ref, C))}", flush=True)
-    if mode == 0: pass
+        print(f"split {split} panels {panels}: {ms:.3f} ms  same={bool(torch.equal(ref, C))}", flush=True)
