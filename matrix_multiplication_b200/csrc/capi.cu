@@ -304,8 +304,9 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "host_copy_ctas")) { options().host_copy_ctas = (int)value; return B200_OK; }
   if (!strcmp(name, "host_copy_split")) { options().host_copy_split = (int)value; return B200_OK; }
   if (!strcmp(name, "tail_tasks")) { options().tail_tasks = (int)std::max<int64_t>(0, value); return B200_OK; }
+  if (!strcmp(name, "d2c_lag")) { options().d2c_lag = (int)value; return B200_OK; }
   if (!strcmp(name, "d2c_warps")) {
-    B200_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8 || value == 16, "d2c_warps must be 0, 2, 4, 8 or 16");
+    B200_REQUIRE(value == 0 || value == 16 || value == 20 || value == 24, "d2c_warps must be 0, 16, 20 or 24");
     options().d2c_warps = (int)value; return B200_OK;
   }
   if (!strcmp(name, "tc_mode")) { options().tc_mode = (int)value; return B200_OK; }
@@ -335,6 +336,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "host_copy_split")) return options().host_copy_split;
   if (!strcmp(name, "tail_tasks")) return options().tail_tasks;
   if (!strcmp(name, "d2c_warps")) return options().d2c_warps;
+  if (!strcmp(name, "d2c_lag")) return options().d2c_lag;
   if (!strcmp(name, "tc_mode")) return options().tc_mode;
   if (!strcmp(name, "tc_nt")) return options().tc_nt;
   if (!strcmp(name, "tc_terms")) return options().tc_terms;

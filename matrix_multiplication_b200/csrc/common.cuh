@@ -57,7 +57,8 @@ struct Options {
   int host_copy_ctas = 32; // CTAs of one SM-driven panel copy
   int host_copy_split = 1; // row chunks (= copy engines) per panel copy of the host pipeline
   int tail_tasks = 0;      // short tasks (W/4) at the end of a forward launch; measured no gain on config 4 and its shards (profiles/r2_scaling.md): off
-  int d2c_warps = 0;       // dense->CSR one-pass tile size in warps (2, 4, 8, 16; 0 = default 4)
+  int d2c_warps = 0;       // dense->CSR one-pass: count warps per CTA (16, 20, 24; 0 = default 24), the other warps: offset + fill
+  int d2c_lag = 0;         // dense->CSR one-pass experiments: low byte 1 = small pair rings; bit 8 = count side alone (wrong results)
   // block-dense tensor-core path (tc_gemm.cu)
   int tc_mode = 1;         // 0 = never, 1 = auto (density / N rule), 2 = whenever the shape allows it
   int tc_nt = 0;           // tile width override (multiple of 32, <= 256); 0 = auto

@@ -297,11 +297,15 @@ void tiledspmm_clean() {
 }
 
 // ---- engine extras used by matmuls.py (not in the reference's module) ------------------------
-// dense -> CSR.  Default: the two-phase pair (count, exact allocation, fill) — measured faster than the one-pass
-// kernel on a B200 (16384^2: 0.42-0.70 ms vs 0.86-1.3 ms, profiles/r2_dense2csr.md: the cross-CTA look-back of the
-// one-pass kernel stalls its tiles).  set_onepass_max_elems(n) routes matrices of up to n elements through the
-// one-pass kernel (worst-case sized outputs, 8 bytes per dense element; compact = true returns right-sized copies).
-int64_t g_onepass_max_elems = 0;
+// dense -> CSR.  Large matrices go through the one-pass kernel (count warps / offset warp / fill warps, the dense
+// matrix leaves HBM once; profiles/r2_dense2csr.md: 16384^2 at 90 / 99 / 99.9 % sparsity 0.35 / 0.28 / 0.22 ms against
+// 0.49 / 0.43 / 0.42 ms for count + fill).  Its outputs are sized for one kept element in eight (the kept fraction is not
+// known before the pass); a denser matrix is reported by the kernel with row_ptr complete, and the exact-size fill
+// finishes the job.  The kept fraction of the previous conversion is remembered: after a dense one (> 1/8) the
+// two-phase pair is used directly (it is the faster one there).  Small matrices stay on the two-phase pair
+// (launch-bound either way).  set_onepass_min_elems(n): threshold in elements (default 2^20; < 0 = never).
+int64_t g_onepass_min_elems = 1 << 20;
+double g_last_kept_fraction = 0.0;
 std::vector<torch::Tensor> dense_to_csr(torch::Tensor dense, bool compact) {
   check_dense(dense, "dense");
   c10::cuda::CUDAGuard guard(dense.device());
@@ -309,25 +313,32 @@ std::vector<torch::Tensor> dense_to_csr(torch::Tensor dense, bool compact) {
   auto iopt = torch::dtype(torch::kInt32).device(dense.device());
   auto crow = torch::empty({M + 1}, iopt);
   int64_t nnz = 0;
-  if (M * K > 0 && M * K <= g_onepass_max_elems) {
-    // one pass over the dense matrix into worst-case sized arrays (the caching allocator hands them out without a
-    // cudaMalloc after the first call); the results are views of the first nnz entries
-    auto col = torch::empty({M * K}, iopt);
-    auto val = torch::empty({M * K}, dense.options());
+  const int64_t ld = ld_of(dense);
+  const bool onepass = g_onepass_min_elems >= 0 && M * K >= std::max<int64_t>(g_onepass_min_elems, 1) && K >= 64 &&
+                       ld % 4 == 0 && reinterpret_cast<uintptr_t>(dense.data_ptr<float>()) % 16 == 0 &&
+                       g_last_kept_fraction <= 0.125;
+  if (onepass) {
+    const int64_t cap = std::max<int64_t>(M * K / 8, 4096);
+    auto col = torch::empty({cap}, iopt);
+    auto val = torch::empty({cap}, dense.options());
     const size_t sb = b200_dense_to_csr_onepass_scratch_bytes(M, K);
     auto scratch = torch::empty({(int64_t)sb}, torch::dtype(torch::kUInt8).device(dense.device()));
-    check(b200_dense_to_csr_onepass(dense.data_ptr<float>(), M, K, ld_of(dense), crow.data_ptr<int>(),
-                                    col.data_ptr<int>(), val.data_ptr<float>(), M * K, scratch.data_ptr(), sb, &nnz,
-                                    cur_stream()));
-    if (compact) return {crow, col.narrow(0, 0, nnz).clone(), val.narrow(0, 0, nnz).clone()};
-    return {crow, col.narrow(0, 0, nnz), val.narrow(0, 0, nnz)};
+    const int rc = b200_dense_to_csr_onepass(dense.data_ptr<float>(), M, K, ld, crow.data_ptr<int>(), col.data_ptr<int>(),
+                                             val.data_ptr<float>(), cap, scratch.data_ptr(), sb, &nnz, cur_stream());
+    if (rc == B200_OK) {
+      g_last_kept_fraction = (double)nnz / (double)(M * K);
+      if (compact) return {crow, col.narrow(0, 0, nnz).clone(), val.narrow(0, 0, nnz).clone()};
+      return {crow, col.narrow(0, 0, nnz), val.narrow(0, 0, nnz)};
+    }
+    if (nnz <= cap) check(rc);  // a real failure; otherwise: denser than the guess, row_ptr is complete
+  } else {
+    check(b200_dense_to_csr_count(dense.data_ptr<float>(), M, K, ld, crow.data_ptr<int>(), &nnz, cur_stream()));
   }
-  check(b200_dense_to_csr_count(dense.data_ptr<float>(), M, K, ld_of(dense), crow.data_ptr<int>(), &nnz,
-                                cur_stream()));
+  if (M * K > 0) g_last_kept_fraction = (double)nnz / (double)(M * K);
   auto col = torch::empty({nnz}, iopt);
   auto val = torch::empty({nnz}, dense.options());
-  check(b200_dense_to_csr_fill(dense.data_ptr<float>(), M, K, ld_of(dense), crow.data_ptr<int>(),
-                               col.data_ptr<int>(), val.data_ptr<float>(), cur_stream()));
+  check(b200_dense_to_csr_fill(dense.data_ptr<float>(), M, K, ld, crow.data_ptr<int>(), col.data_ptr<int>(),
+                               val.data_ptr<float>(), cur_stream()));
   return {crow, col, val};
 }
 
@@ -537,7 +548,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // engine extras
   m.def("dense_to_csr", &dense_to_csr, "dense [M,K] -> (crow int32, col int32, val) on the device",
         py::arg("dense"), py::arg("compact") = false);
-  m.def("set_onepass_max_elems", [](int64_t n) { g_onepass_max_elems = n; });
+  m.def("set_onepass_min_elems", [](int64_t n) { g_onepass_min_elems = n; g_last_kept_fraction = 0.0; },
+        "one-pass dense->CSR for matrices of at least n elements (< 0: never); also forgets the remembered density");
   m.def("dense_to_csr_block_diag", &dense_to_csr_block_diag,
         "stack of L dense [M,K] matrices given as [L*M,K] -> block-diagonal CSR (crow, col, val) of [L*M, L*K]");
   m.def("csr_transpose", &csr_transpose, "CSR(A) -> (crow, col, val, perm) of A^T");

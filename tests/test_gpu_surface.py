@@ -325,6 +325,40 @@ def test_batched_product_is_one_launch(mods):
     assert torch.allclose(a2.grad.double(), ones @ b.double().transpose(-1, -2), rtol=1e-4, atol=1e-4)
 
 
+def test_dense_to_csr_adaptive_one_pass(mods):
+    """custom_mm.dense_to_csr on large matrices: the one-pass kernel for sparse inputs, its capacity overflow (denser
+    than one kept element in eight) finished by the exact fill, the remembered density sending the next dense
+    conversion straight to the two-phase pair — every route bit-identical to torch.to_sparse_csr."""
+    torch, custom_mm, _ = mods
+    torch.manual_seed(11)
+
+    def check(d, compact=False):
+        crow, col, val = custom_mm.dense_to_csr(d, compact)
+        t = d.contiguous().to_sparse_csr()
+        assert torch.equal(crow.long(), t.crow_indices())
+        assert torch.equal(col.long(), t.col_indices())
+        assert torch.equal(val.view(torch.int32), t.values().view(torch.int32))
+
+    custom_mm.set_onepass_min_elems(1 << 20)                        # (also forgets the remembered density)
+    base = torch.randn(1500, 2052, device="cuda")
+    keep = torch.rand(1500, 2052, device="cuda")
+    for dens in (0.001, 0.02, 0.1):                                  # one pass: compacted chunks
+        check((base * (keep < dens))[:, :2048])                      # ld = 2052: strided rows, 16-byte aligned
+    sparse = base * (keep < 0.02)
+    sparse[3] = 0
+    sparse[4] = 2.5                                                  # a full row inside a sparse matrix: re-read chunks
+    sparse[5, 7] = float("nan")
+    sparse[6, 9] = -0.0
+    check(sparse, compact=True)
+    check(base * (keep < 0.5))                                       # overflow: one pass, then the exact fill
+    check(base * (keep < 0.5))                                       # remembered: two-phase directly
+    check(base * (keep < 0.01))                                      # (still two-phase: one sparse result re-arms)
+    check(base * (keep < 0.01))                                      # one pass again
+    custom_mm.set_onepass_min_elems(-1)
+    check(base * (keep < 0.01))                                      # never
+    custom_mm.set_onepass_min_elems(1 << 20)
+
+
 @pytest.mark.parametrize("K,ld", [(130, 132), (129, 132), (131, 256), (4, 8), (5, 8), (1000, 1024), (4096, 4096)])
 def test_dense_to_csr_strided_and_ragged_widths(mods, K, ld):
     """The 128-bit fill path (ld % 4 == 0) with K not a multiple of 4 / of 128, on a strided view."""

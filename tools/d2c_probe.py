@@ -16,7 +16,7 @@ def timeit(fn, iters=10):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts)//2]
 M = K = 16384
-for sp in (0.5, 0.9, 0.99, 0.999):
+for sp in (0.9, 0.99, 0.999):
     g = torch.Generator(device=dev).manual_seed(0)
     d = torch.rand(M, K, device=dev, generator=g) * (torch.rand(M, K, device=dev, generator=g) >= sp)
     crow = torch.empty(M + 1, dtype=torch.int32, device=dev)
@@ -30,10 +30,19 @@ for sp in (0.5, 0.9, 0.99, 0.999):
     def twopass():
         capi.check(capi.lib().b200_dense_to_csr_count(d.data_ptr(), M, K, K, crow.data_ptr(), None, None))
         capi.check(capi.lib().b200_dense_to_csr_fill(d.data_ptr(), M, K, K, crow.data_ptr(), col.data_ptr(), val.data_ptr(), None))
-    for wv in (2, 4, 8, 16):
-        capi.set_option("d2c_warps", wv)
-        print(f"  d2c_warps {wv}: {timeit(onepass):.4f} ms", flush=True)
-    capi.set_option("d2c_warps", 0)
+    for wv in (8, 16, 24):
+        for lag in (0, 6):
+            capi.set_option("d2c_warps", wv); capi.set_option("d2c_lag", lag)
+            print(f"  count warps {wv} lag {lag}: {timeit(onepass):.4f} ms", flush=True)
+    for wv in (8, 16, 24):
+        capi.set_option("d2c_warps", wv); capi.set_option("d2c_lag", 6 + 256)
+        print(f"  count warps {wv} count side alone (no fill, no gating): {timeit(onepass):.4f} ms", flush=True)
+    capi.set_option("d2c_warps", 0); capi.set_option("d2c_lag", 0)
+    twopass(); torch.cuda.synchronize()
+    c2, v2, r2 = col.clone(), val.clone(), crow.clone()
+    col.zero_(); val.zero_(); crow.zero_()
+    onepass(); torch.cuda.synchronize()
+    print("  one-pass == two-pass:", bool(torch.equal(c2, col) and torch.equal(v2.view(torch.int32), val.view(torch.int32)) and torch.equal(r2, crow)), flush=True)
     t1, t2 = timeit(onepass), timeit(twopass)
     t3 = timeit(lambda: custom_mm.dense_to_csr(d))
     by = 4.0 * M * K + 4 * (M + 1) + 8.0 * nnz
