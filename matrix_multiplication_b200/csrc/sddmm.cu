@@ -148,50 +148,37 @@ sddmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int M
         for (int k = 0; k < 8; ++k)
 #pragma unroll
           for (int v = 0; v < VEC; ++v) d[k] = fmaf(gcur.v[v], b[k].v[v], d[k]);
-      } else {  // mixed chunk (row ends inside it, or a task edge), in two halves of 4 so that only 4 B slabs +
-        // 4 G slabs are live at a time (register budget = occupancy here).  Rows are sorted, so a G slab is
-        // gathered only where the row changes (and not at all for the row carried over from the previous chunk):
-        // `g` runs along the non-zeros and is replaced by a freshly gathered slab at every row start — a uniform
-        // select after the loads have landed, so nothing waits on a register move.
-        Vec<VEC> g = gcur;
-        int run_row = n_slabs == 1 ? cur_row : -1;  // row whose G slab is in g
+      } else {  // mixed chunk (row ends inside it, or a task edge): one G gather per non-zero, in two halves
+        // of 4 so that only 4 B slabs + 4 G slabs are live at a time (register budget = occupancy here)
+        Vec<VEC> g4[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          Vec<VEC> b4[4], g4[4];
-          bool fresh[4];
+          Vec<VEC> b4[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int kk = 4 * h + k;
-            fresh[k] = false;
             if ((vm >> kk) & 1u) {
               b4[k].load(B + (unsigned long long)(unsigned)c[kk] * ldb + cc);
-              const int rk = s_row[off + kk];
-              if (rk != run_row) {
-                g4[k].load(G + (unsigned long long)(unsigned)rk * ldg + cc);
-                fresh[k] = true;
-                run_row = rk;
-              }
+              g4[k].load(G + (unsigned long long)(unsigned)s_row[off + kk] * ldg + cc);
             } else {
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) b4[k].v[v] = 0.f;
+              for (int v = 0; v < VEC; ++v) { b4[k].v[v] = 0.f; g4[k].v[v] = 0.f; }
             }
           }
-          if (!active) {  // lanes beyond column N read column 0: both factors are zeroed (a 0 * Inf must not appear)
+          if (!active) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) { b4[k].v[v] = 0.f; g4[k].v[v] = 0.f; }
+              for (int v = 0; v < VEC; ++v) g4[k].v[v] = 0.f;
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (fresh[k]) g = g4[k];
+          for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) d[4 * h + k] = fmaf(g.v[v], b4[k].v[v], d[4 * h + k]);
-          }
+            for (int v = 0; v < VEC; ++v) d[4 * h + k] = fmaf(g4[k].v[v], b4[k].v[v], d[4 * h + k]);
         }
-        if (n_slabs == 1) {
-          cur_row = run_row;
-          gcur = g;
+        if (n_slabs == 1 && ((vm >> 7) & 1u)) {
+          cur_row = r7;
+          gcur = g4[3];
         } else {
           cur_row = -1;
         }
