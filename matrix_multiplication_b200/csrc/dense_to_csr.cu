@@ -484,7 +484,7 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
     long long carry = 0;  // kept elements of all earlier rounds (every CTA keeps its own copy)
     auto one_round = [&](int i, unsigned (&v)[PF], unsigned (&v1)[PF], unsigned (&v2)[PF]) {
       while (!complete(i, v)) {
-        __nanosleep(40);
+        __nanosleep(100);
         refresh(i, v);
         refresh(i + 1, v1);
         refresh(i + 2, v2);
@@ -520,7 +520,7 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
       if (lane < NC) {
         int t = *(volatile int*)&s_tot[slot][lane];
         while ((t >> 11) != i + 1) {
-          __nanosleep(20);
+          __nanosleep(60);
           t = *(volatile int*)&s_tot[slot][lane];
         }
         mine = t & 0x7ff;
@@ -550,7 +550,7 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
   const int wf = warp - NC - 1;
   for (int i = 0; i < rounds; ++i) {
     const int slot = i % R;
-    while (*(volatile int*)&s_off_tag[slot] != i + 1) __nanosleep(32);
+    while (*(volatile int*)&s_off_tag[slot] != i + 1) __nanosleep(200);
     __threadfence_block();
     for (int k = wf; k < NC; k += NF) {
       const long long chunk = ((long long)i * G + b) * NC + k;

@@ -16,7 +16,7 @@ def timeit(fn, iters=10):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts)//2]
 M = K = 16384
-for sp in (0.9, 0.99, 0.999):
+for sp in (0.5, 0.9, 0.99, 0.999):
     g = torch.Generator(device=dev).manual_seed(0)
     d = torch.rand(M, K, device=dev, generator=g) * (torch.rand(M, K, device=dev, generator=g) >= sp)
     crow = torch.empty(M + 1, dtype=torch.int32, device=dev)
@@ -30,12 +30,12 @@ for sp in (0.9, 0.99, 0.999):
     def twopass():
         capi.check(capi.lib().b200_dense_to_csr_count(d.data_ptr(), M, K, K, crow.data_ptr(), None, None))
         capi.check(capi.lib().b200_dense_to_csr_fill(d.data_ptr(), M, K, K, crow.data_ptr(), col.data_ptr(), val.data_ptr(), None))
-    for wv in (8, 16, 24):
-        for lag in (0, 6):
-            capi.set_option("d2c_warps", wv); capi.set_option("d2c_lag", lag)
-            print(f"  count warps {wv} lag {lag}: {timeit(onepass):.4f} ms", flush=True)
-    for wv in (8, 16, 24):
-        capi.set_option("d2c_warps", wv); capi.set_option("d2c_lag", 6 + 256)
+    for wv in (16, 20, 24):
+        for small in (0, 1):
+            capi.set_option("d2c_warps", wv); capi.set_option("d2c_lag", small)
+            print(f"  count warps {wv} pair ring {256 if small else 512}: {timeit(onepass):.4f} ms", flush=True)
+    for wv in (16, 20, 24):
+        capi.set_option("d2c_warps", wv); capi.set_option("d2c_lag", 256)
         print(f"  count warps {wv} count side alone (no fill, no gating): {timeit(onepass):.4f} ms", flush=True)
     capi.set_option("d2c_warps", 0); capi.set_option("d2c_lag", 0)
     twopass(); torch.cuda.synchronize()
@@ -44,6 +44,7 @@ for sp in (0.9, 0.99, 0.999):
     onepass(); torch.cuda.synchronize()
     print("  one-pass == two-pass:", bool(torch.equal(c2, col) and torch.equal(v2.view(torch.int32), val.view(torch.int32)) and torch.equal(r2, crow)), flush=True)
     t1, t2 = timeit(onepass), timeit(twopass)
+    custom_mm.set_onepass_min_elems(1 << 20)
     t3 = timeit(lambda: custom_mm.dense_to_csr(d))
     by = 4.0 * M * K + 4 * (M + 1) + 8.0 * nnz
-    print(f"sparsity {sp}: nnz {nnz}  one-pass {t1:.4f} ms ({by/t1/1e6:.0f} GB/s, {by/t1/1e6/6549.1:.3f} of roof)  two-pass {t2:.4f} ms ({by/t2/1e6/6549.1:.3f})  custom_mm.dense_to_csr (alloc + sync) {t3:.4f} ms", flush=True)
+    print(f"sparsity {sp}: nnz {nnz}  one-pass {t1:.4f} ms ({by/t1/1e6:.0f} GB/s, {by/t1/1e6/6549.1:.3f} of roof)  two-pass {t2:.4f} ms ({by/t2/1e6/6549.1:.3f})  custom_mm.dense_to_csr (adaptive; alloc + sync) {t3:.4f} ms", flush=True)
