@@ -320,10 +320,9 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
   constexpr int R = 16;          // rounds a CTA may have between "counted" and "written" (bookkeeping rings)
   constexpr int DENSE_LAG = 3;   // ... when the chunk will be re-read by the fill warps (it has to stay in the L2)
   extern __shared__ __align__(16) unsigned char op_smem[];
-  // per count warp a ring of P compacted (column, value) pairs: [NC][P] columns, then the same for values; then the
+  // per count warp a ring of P compacted (column, value) pairs: [NC][P] x 8 bytes; then the
   // count warps' landing slots for raw chunks: [NC][D][OP_CHUNK] floats, filled by TMA bulk copies
-  int* s_col = reinterpret_cast<int*>(op_smem);
-  float* s_val = reinterpret_cast<float*>(op_smem + (size_t)NC * P * 4);
+  uint2* s_pair = reinterpret_cast<uint2*>(op_smem);  // (column, value bits)
   float* s_raw = reinterpret_cast<float*>(op_smem + (size_t)NC * P * 8);
   __shared__ __align__(8) uint64_t s_bar[NC][D];
   __shared__ int s_tot[R][NC];         // chunk totals, tagged with the round: ((round + 1) << 11) | total
@@ -418,8 +417,7 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
           while (head + (unsigned)cnt - *(volatile unsigned*)&s_tail[warp] > (unsigned)P) __nanosleep(32);
       }
       if (small) {
-        int* pc = s_col + (size_t)warp * P;
-        float* pv = s_val + (size_t)warp * P;
+        uint2* pp = s_pair + (size_t)warp * P;
         unsigned gbase = head;  // ring position of the group's first kept element
 #pragma unroll
         for (int u = 0; u < OP_G; ++u) {
@@ -432,8 +430,7 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (keep(e[j])) {
-                pc[q & (unsigned)(P - 1)] = c + j;
-                pv[q & (unsigned)(P - 1)] = e[j];
+                pp[q & (unsigned)(P - 1)] = make_uint2((unsigned)(c + j), __float_as_uint(e[j]));
                 ++q;
               }
           }
@@ -562,14 +559,14 @@ onepass_kernel(const float* __restrict__ dense, int M, int K, long long ld, int 
       if (c0 == 0 && lane == 0) row_ptr[row] = (int)base;
       if (total == 0) continue;
       if (total <= OP_SMALL) {
-        const int* pc = s_col + (size_t)k * P;
-        const float* pv = s_val + (size_t)k * P;
+        const uint2* pp = s_pair + (size_t)k * P;
         const unsigned start = s_start[slot][k];
         for (int idx = lane; idx < total; idx += 32) {
           const long long q = base + idx;
           if (q < capacity) {
-            col[q] = pc[(start + (unsigned)idx) & (unsigned)(P - 1)];
-            val[q] = pv[(start + (unsigned)idx) & (unsigned)(P - 1)];
+            const uint2 pr = pp[(start + (unsigned)idx) & (unsigned)(P - 1)];
+            col[q] = (int)pr.x;
+            val[q] = __uint_as_float(pr.y);
           }
         }
         __syncwarp();
