@@ -34,23 +34,27 @@ def shard_bounds(row_ptr, parts: int, N: int, miss: float = 0.29) -> np.ndarray:
     return capi.shard_rows(row_ptr, parts, 8.0 + 4.0 * N * miss, 4.0 * N)
 
 
-def rebalance_bounds(row_ptr, bounds, times, N: int, miss: float = 0.29) -> np.ndarray:
+def rebalance_bounds(row_ptr, bounds, times, N: int, miss: float = 0.29, fixed_ms: float = 0.02) -> np.ndarray:
     '''New row boundaries from MEASURED per-shard times (inspector step of a multi-GPU plan: every rank times its own
-    shard during warm-up, the times are all-gathered, the rows are re-cut).  The model cost of a row,
-    nnz * (8 + 4N * miss) + 4N, is scaled inside every current shard by (measured time / model cost of the shard), and
-    the boundaries move to the equal quantiles of that corrected cumulative cost.  One or two rounds bring
-    max/mean of the shard times to ~1.02 on the R-MAT matrix (the static model leaves ~1.06: rows that are split
-    into pieces cost more than it assumes).'''
+    shard during warm-up, the times are all-gathered, the rows are re-cut).  A shard's time is a fixed part (launch,
+    first-wave staging, last-wave drain: `fixed_ms`, 0.02 ms measured on the gather kernels, profiles/r2_scaling.md)
+    plus a part that follows its rows; the model cost of a row, nnz * (8 + 4N * miss) + 4N, is scaled inside every
+    current shard by (measured time - fixed part) / (model cost of the shard), and the boundaries move to the equal
+    quantiles of that corrected cumulative cost.  (Scaling by the whole time, as the first version did, under-corrects:
+    moving rows only moves the variable part.)  The caller probes a few rounds and keeps the best boundaries it saw
+    (bench.py): max/mean of the shard times ~1.01-1.02 on the R-MAT matrix (static model: ~1.05).'''
     row_ptr = np.asarray(row_ptr, dtype=np.int64)
     bounds = np.asarray(bounds, dtype=np.int64)
     parts = len(bounds) - 1
     M = len(row_ptr) - 1
     cost = np.diff(row_ptr).astype(np.float64) * (8.0 + 4.0 * N * miss) + 4.0 * N
+    tmin = min(float(t) for t in times) if len(times) else 0.0
+    fixed = min(float(fixed_ms), 0.5 * tmin) if tmin > 0 else 0.0  # never more than half of the fastest shard
     for g in range(parts):
         r0, r1 = int(bounds[g]), int(bounds[g + 1])
         c = cost[r0:r1].sum()
         if c > 0 and times[g] > 0:
-            cost[r0:r1] *= float(times[g]) / c
+            cost[r0:r1] *= (float(times[g]) - fixed) / c
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     targets = cum[-1] * np.arange(1, parts) / parts
     new = np.concatenate([[0], np.searchsorted(cum, targets, side='left'), [M]]).astype(np.int64)
