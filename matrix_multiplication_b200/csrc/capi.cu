@@ -132,6 +132,7 @@ struct b200_plan {
   int last_path = 0;                   // 0 gather kernels, 1 tensor-core tiles, 2 strided fallback
   SlabStore slab[2];                   // narrow-N slab kernel state per side (built for one N at a time)
   bool slab_built[2] = {false, false};
+  bool slab_stale[2] = {false, false};  // values changed since the sliced stream was written
   TcSample samp;                       // A's pattern as bit masks, for the tensor-core SDDMM's sampling epilogue
   bool samp_built = false, samp_failed = false;
   void* sd_ws = nullptr;               // packed G and B of the tensor-core SDDMM
@@ -592,6 +593,7 @@ int b200_plan_values_updated(b200_plan* p) {
   B200_REQUIRE(p != nullptr, "null plan");
   p->t_val_stale = true;
   p->tc_stale[0] = p->tc_stale[1] = true;
+  p->slab_stale[0] = p->slab_stale[1] = true;
   return B200_OK;
 }
 
@@ -732,7 +734,7 @@ static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* c
   if (rc) return rc;
   bool want_tc = plan_wants_tc(p, M, K, N, flags);
   // narrow dense operand whose rows fit a few shared-memory slabs: ~15 us + nnz / 4.0e5 us on the slab kernel
-  const bool slab_ok = !bt && !ct && options().slab_mode == 1 && !(flags & B200_OP_FORCE_TC) &&
+  const bool slab_ok = !bt && !ct && options().slab_mode >= 1 && !(flags & B200_OP_FORCE_TC) &&
                        slab_wanted(M, K, p->nnz, (int)N, d_B, ldb, d_C, ldc);
   if (slab_ok && want_tc && 15.0 + (double)p->nnz / 4.0e5 < g_last_tc_estimate_us) want_tc = false;
   if (want_tc) {
@@ -765,11 +767,16 @@ static int plan_spmm_ex(b200_plan* p, int side, const int* row_ptr, const int* c
   }
   if (slab_ok) {
     // gather from shared-memory slabs of B instead of L1 / L2
-    if (!p->slab_built[side] || p->slab[side].N != (int)N) {
+    if (!p->slab_built[side] || p->slab[side].N != (int)N || p->slab[side].v2 != (options().slab_mode != 2)) {
       if (p->slab_built[side]) { B200_CUDA_OK(cudaStreamSynchronize(s)); slab_store_free(&p->slab[side]); p->slab_built[side] = false; }
-      rc = slab_store_build(row_ptr, col, M, K, p->nnz, (int)N, &p->slab[side], s);
+      rc = slab_store_build(row_ptr, col, val, M, K, p->nnz, (int)N, &p->slab[side], s);
       if (rc) return rc;
       p->slab_built[side] = true;
+      p->slab_stale[side] = false;
+    } else if (p->slab_stale[side]) {  // values changed in place: rewrite the stream
+      rc = slab_store_refresh(col, val, &p->slab[side], s);
+      if (rc) return rc;
+      p->slab_stale[side] = false;
     }
     p->last_path = 3;
     return launch_spmm_slab(p->slab[side], col, val, d_B, d_C, ldc, d_bias, relu ? 1 : 0, s);

@@ -52,7 +52,7 @@ struct Options {
   int flat_min_n = 24;     // smallest N served by the flat (one lane group) kernel
   int pipeline = 0;        // flat kernel variant: 0 = shipped; 1 = 8 warps/CTA; 2, 3 = 16 / 24 gathers per warp
                            // (the alternatives of profiles/r1_variant_sweep.md, kept for re-measurement)
-  int slab_mode = 1;       // narrow-N shared-memory slab kernel: 0 = never, 1 = when slab_wanted() says so
+  int slab_mode = 1;       // narrow-N shared-memory slab kernel: 0 = never, 1 = when slab_wanted() says so (sliced stream, v2), 2 = same with the first kernel (CSR walked in place), 3 = v2 whenever the shape allows it (probing)
   int host_copy_mode = 0;  // b200_plan_forward_host panel copies: 0 = copy engine (cudaMemcpy2DAsync), 1 = SM copy kernel
   int host_copy_ctas = 32; // CTAs of one SM-driven panel copy
   int host_copy_split = 1; // row chunks (= copy engines) per panel copy of the host pipeline
@@ -342,10 +342,20 @@ int launch_tc_forward(const TcStore& st, const int* row_ptr, const int* col, con
 struct SlabStore {
   int N = 0, M = 0, K = 0, S = 0, rows_per_slab = 0, G = 0;
   int* slab_ptr = nullptr;  // [M][S + 1] first non-zero of a row at or beyond every slab boundary
-  int* cta_rows = nullptr;  // [G + 1] first row of every persistent CTA
+  int* cta_rows = nullptr;  // v1: [G + 1] first row of every persistent CTA
+  // v2 (default): a slab-major, sliced copy of A (spmm_slab.cu)
+  bool v2 = false;
+  int HR = 0, pass_rows = 0, n_slices = 0, total_steps = 0;
+  int* vis_off = nullptr;     // [n_slices * S + 1] exclusive prefix of the blocks of every visit, consumption order
+  int* cell_gv = nullptr;     // [n_slices * S] visit index of every (slice, slab)
+  int* warp_vis = nullptr;    // [G * 32 + 1] first visit of every warp
+  int* cta_slices = nullptr;  // [G + 1] first slice of every persistent CTA
+  uint4* stream = nullptr;    // [total_steps / 2][32 / (N / 4)] blocks of 2 steps: (col0, val0, col1, val1)
 };
 bool slab_wanted(int M, int K, long long nnz, int N, const float* B, long long ldb, const float* C, long long ldc);
-int slab_store_build(const int* row_ptr, const int* col, int M, int K, int nnz, int N, SlabStore* st, cudaStream_t s);
+int slab_store_build(const int* row_ptr, const int* col, const float* val, int M, int K, int nnz, int N, SlabStore* st,
+                     cudaStream_t s);
+int slab_store_refresh(const int* col, const float* val, SlabStore* st, cudaStream_t s);
 void slab_store_free(SlabStore* st);
 int launch_spmm_slab(const SlabStore& st, const int* col, const float* val, const float* B, float* C, long long ldc,
                      const float* bias, int relu, cudaStream_t s);

@@ -166,8 +166,22 @@ def test_forward_narrow_n_slab_kernel(case):
     Cb = plan.forward_ex(Bd, torch.empty(M, N, device=dev), bias=bd, flags=capi.OP_NO_TC | capi.OP_RELU)
     torch.cuda.synchronize()
     assert oracle.rel_err(Cb.cpu().numpy(), np.maximum(ref + bias[:, None].astype(np.float64), 0.0)) <= TOL
-    capi.set_option("slab_mode", 0)
+    # values changed in place: the plan's sliced copy of A is rewritten after b200_plan_values_updated
+    val.mul_(-2.0)
+    plan.values_updated()
+    Cn = plan.forward_ex(Bd, torch.empty(M, N, device=dev), flags=capi.OP_NO_TC)
+    torch.cuda.synchronize()
+    assert plan.tc_info()["last_path"] == 3
+    assert oracle.rel_err(Cn.cpu().numpy(), -2.0 * ref) <= TOL
+    val.mul_(-0.5)
+    plan.values_updated()
     try:
+        capi.set_option("slab_mode", 2)  # the first slab kernel (CSR walked in place)
+        C1 = plan.forward_ex(Bd, torch.empty(M, N, device=dev), flags=capi.OP_NO_TC)
+        torch.cuda.synchronize()
+        assert plan.tc_info()["last_path"] == 3
+        assert oracle.rel_err(C1.cpu().numpy(), ref) <= TOL
+        capi.set_option("slab_mode", 0)
         Cg = plan.forward_ex(Bd, torch.empty(M, N, device=dev), flags=capi.OP_NO_TC)
         torch.cuda.synchronize()
         assert plan.tc_info()["last_path"] == 0
