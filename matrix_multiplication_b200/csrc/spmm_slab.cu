@@ -363,17 +363,39 @@ spmm_slab2_kernel(const uint4* __restrict__ stream, const int* __restrict__ vis_
   const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(stream) + (size_t)wb0 * BLK;
   unsigned char* wring = ring + (size_t)warp * RC * CHB;
   uint64_t* wbar = rbar + warp * RC;
+  // (everything below works on 32-bit shared-window addresses: no generic-pointer arithmetic in the hot loop)
+  const uint32_t wring_s = smem_u32(wring), wbar_s = smem_u32(wbar);
+  uint64_t policy;  // the stream is read exactly once: evict-first in L2
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   auto issue_chunk = [&](int ci) {  // lane 0: chunk ci of this warp's stream -> ring slot ci % RC
-    const uint32_t bytes = (uint32_t)min(CB, nblk - ci * CB) * BLK;
-    mbar_expect_tx(wbar + ci % RC, bytes);
-    tma_bulk_g2s_stream(wring + (size_t)(ci % RC) * CHB, wsrc + (size_t)ci * CHB, bytes, wbar + ci % RC);
+    const int rem = nblk - ci * CB;
+    const uint32_t bytes = (uint32_t)(rem >= CB ? CB : rem) * BLK;
+    const uint32_t sl = (uint32_t)ci & (RC - 1);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar_s + sl * 8u), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            wring_s + sl * CHB),
+        "l"(wsrc + (size_t)ci * CHB), "r"(bytes), "r"(wbar_s + sl * 8u), "l"(policy)
+        : "memory");
+  };
+  auto wait_chunk = [&](uint32_t sl, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t"
+        "}" ::"r"(wbar_s + sl * 8u),
+        "r"(parity)
+        : "memory");
   };
   if (lane == 0)
     for (int ci = 0; ci < RC && ci < nchunks; ++ci) issue_chunk(ci);
   // position in the stream: chunk ci (ring slot, phase of its barrier), cb blocks of it consumed, byte offset in the ring
   int ci = 0, slot = 0, cb = 0;
   uint32_t rphase = 0u, roff = 0u;
-  const uint32_t ring_s = smem_u32(wring) + 16u * g;
+  const uint32_t ring_s = wring_s + 16u * g;
+  static_assert((RC & (RC - 1)) == 0, "ring slots are addressed with a mask");
 
   uint32_t phase0 = 0u, phase1 = 0u;
   auto issue_slab = [&](int s, int b) {  // thread 0: rows [s * rps, min(K, (s+1) * rps)) of B -> buffer b
@@ -409,7 +431,7 @@ spmm_slab2_kernel(const uint4* __restrict__ stream, const int* __restrict__ vis_
         if (nb == 0) continue;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < nb; ++k) {
-          if (cb == 0) mbar_wait(wbar + slot, rphase);  // first block of a chunk: has its copy landed?
+          if (cb == 0) wait_chunk((uint32_t)slot, rphase);  // first block of a chunk: has its copy landed?
           const uint4 cur = lds128_u(ring_s + roff);
           const float4 b0 = lds128_f(slab_s + cur.x * (N * 4u));
           const float4 b1 = lds128_f(slab_s + cur.z * (N * 4u));
@@ -485,12 +507,12 @@ bool slab_wanted(int M, int K, long long nnz, int N, const float* B, long long l
   if (S > 16) return false;
   if (options().slab_mode == 3) return true;  // (probing) whenever the shape allows it
   if (nnz < (1LL << 20)) return false;
-  // enough non-zeros per (row, slab) visit: below that the per-visit bookkeeping (offsets, group reduction,
+  // enough non-zeros per (row, slab) visit: below that the per-visit bookkeeping (block counts, group reduction,
   // running-sum update, padding of the slices) outweighs the cheaper gathers.  Measured on 16384^2
-  // (profiles/r2_ncu_fwd_n16.md): sliced stream (v2) x16 @99 % (11 per visit) 0.041 vs 0.031 ms on the lane-group
-  // kernel, x8 @99 % (20 per visit) 0.025 vs 0.031, @90 % (110-200 per visit) 0.119 / 0.075 vs 0.217 / 0.206;
+  // (profiles/r2_ncu_fwd_n16.md): sliced stream (v2) x16 @99 % (13 per visit) 0.029 vs 0.031 ms on the lane-group
+  // kernel, x8 @99 % (20 per visit) 0.021 vs 0.031, @90 % (130-200 per visit) 0.105 / 0.070 vs 0.215 / 0.205;
   // first kernel (CSR walked in place): break-even near 48 per visit.
-  return nnz >= (v2 ? 16LL : 48LL) * M * S;
+  return nnz >= (v2 ? 12LL : 48LL) * M * S;
 }
 
 void slab_store_free(SlabStore* st) {
