@@ -569,71 +569,132 @@ __device__ __forceinline__ void csr_order_sddmm(const int* __restrict__ row_ptr,
   }
 }
 
-// Final step of a tile for one epilogue thread: acc[] holds this thread's row (m) x 128-column share of the tile.
+// Final step of a tile for one epilogue warp: acc[] holds this thread's row (m) x 128-column share of the tile.
 // SpMM: scale, + bias, ReLU, store C (or C^T); SDDMM: write the entries that lie on A's pattern.
+// A thread owns a ROW of the tile (TMEM lane = row), so storing from acc[] directly makes every store instruction
+// touch 32 different rows (32 sectors).  Row-major C and the SDDMM's value array are therefore written through a
+// per-warp 32 x 32 transposer in shared memory (`stg`, row stride 33 words: conflict-free both ways): afterwards a
+// lane owns a COLUMN and one instruction writes 32 consecutive words of one row.  C^T needs no transposer (a register
+// is one n, the 32 lanes are 32 consecutive m).
+constexpr int STG_LD = 33;
+constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+constexpr int TC_SMEM_MAX = 227 * 1024;
+
+// What the final step of a tile needs from global memory, fetched in one batch (one round trip, not one per group).
+// Lane = row m for rs / bias / msk / bs; lane = column (of the c-th 32-column group) for cs.
+struct TilePre {
+  float rs, bias;
+  float cs[4];
+  uint32_t msk[4];  // SDDMM: pattern bits of (row m, group c)
+  int bs[4];        //        position of the group's first non-zero in the CSR value array
+};
+
+template <int KIND, bool SDDMM>
+__device__ __forceinline__ void tc_tile_prefetch(const TcParams& p, int mb, int nb, int q, int half, int ntw, int lane,
+                                                 TilePre& t) {
+  const int m = mb * BM + q * 32 + lane;
+  t.rs = 1.f;
+  t.bias = 0.f;
+  if constexpr (SDDMM) {
+    if constexpr (KIND == KIND_F16) t.rs = (m < p.M) ? scale_down(scale_exp(__ldg(p.amax + m))) : 0.f;
+  } else {
+    if constexpr (KIND == KIND_F16) t.rs = (m < p.M) ? __ldg(p.row_scale + m) : 0.f;
+    if (p.bias != nullptr && m < p.M) t.bias = __ldg(p.bias + m);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k0 = nb * p.Nt + half * ntw + c * 32;  // first column of the group (a column of A's pattern for the SDDMM)
+    t.cs[c] = 1.f;
+    t.msk[c] = 0u;
+    t.bs[c] = 0;
+    if (c * 32 < ntw) {
+      if constexpr (SDDMM) {
+        const int grp = k0 >> 5;
+        if (grp < p.groups) {
+          if constexpr (KIND == KIND_F16) t.cs[c] = scale_down(scale_exp(__ldg(p.colmax + k0 + lane)));
+          if (m < p.M) {
+            t.msk[c] = __ldg(p.samp_mask + (size_t)grp * p.M + m);
+            t.bs[c] = __ldg(p.samp_off + (size_t)grp * p.M + m);
+          }
+        }
+      } else {
+        if constexpr (KIND == KIND_F16) t.cs[c] = scale_down(scale_exp((k0 + lane < p.N) ? __ldg(p.colmax + k0 + lane) : 0u));
+      }
+    }
+  }
+}
+
+// SDDMM, one 32-row x 32-column group of one warp: v[j] = this lane's ROW, column j  ->  the entries on A's pattern.
+// Through the warp's transposer: afterwards a lane owns a column and row r's entries are written by one instruction
+// (consecutive words).  No branches in the loop: the unrolled iterations' loads and shuffles issue back to back.
+template <int UNROLL>
+__device__ __forceinline__ void tc_sddmm_group_store(float* __restrict__ out, const float (&v)[32], float rs, float cs,
+                                                     uint32_t mask, int base, int lane, float* __restrict__ stg) {
+  if (!__any_sync(0xffffffffu, mask != 0u)) return;
+  const uint32_t lbit = 1u << lane, lt = lbit - 1u;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = v[j] * rs;
+  stg[lane * STG_LD + 32] = __uint_as_float(mask);  // the pad word of the row carries its mask
+  __syncwarp();
+#pragma unroll UNROLL
+  for (int r = 0; r < 32; ++r) {
+    const uint32_t mr = __float_as_uint(stg[r * STG_LD + 32]);
+    const int br = __shfl_sync(0xffffffffu, base, r);
+    const float x = stg[r * STG_LD + lane] * cs;
+    if (mr & lbit) out[br + __popc(mr & lt)] = x;
+  }
+}
+
 template <int KIND, bool SDDMM>
 __device__ __forceinline__ void tc_tile_store(const TcParams& p, const float (&acc)[128], int mb, int nb, int q, int half,
-                                          int ntw, int lane) {
+                                          int ntw, int lane, float* __restrict__ stg, const TilePre& t) {
   const bool relu = (p.flags & 4u) != 0, ct = (p.flags & 2u) != 0;
-  const bool vec4 = !ct && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-  const int m = mb * BM + q * 32 + lane;
+  const int m0 = mb * BM + q * 32;
+  const int m = m0 + lane;
+  const float rs = t.rs;
   if constexpr (SDDMM) {
     // sample the tile on A's pattern: bit j of the mask <=> (m, 32 g + j) is a non-zero; its position in the CSR
     // value array is the group's offset plus the number of set bits below j
-    float rs = 1.f;
-    if constexpr (KIND == KIND_F16) rs = (m < p.M) ? scale_down(scale_exp(__ldg(p.amax + m))) : 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int k0 = nb * p.Nt + half * ntw + c * 32;
-      const int grp = k0 >> 5;
-      if (c * 32 < ntw && grp < p.groups && m < p.M) {
-        const uint32_t mask = __ldg(p.samp_mask + (size_t)grp * p.M + m);
-        const int base = __ldg(p.samp_off + (size_t)grp * p.M + m);
-        if (mask != 0u) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if ((mask >> j) & 1u) {
-              float x = acc[c * 32 + j];
-              if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp(__ldg(p.colmax + k0 + j)));
-              p.C[base + __popc(mask & ((1u << j) - 1u))] = x;
-            }
-          }
-        }
-      }
+      const int grp = (nb * p.Nt + half * ntw + c * 32) >> 5;
+      if (c * 32 < ntw && grp < p.groups)  // warp-uniform
+        tc_sddmm_group_store<8>(p.C, reinterpret_cast<const float(&)[32]>(acc[c * 32]), rs, t.cs[c], t.msk[c], t.bs[c],
+                                lane, stg);
     }
     return;
   }
-  const float bias = (p.bias != nullptr && m < p.M) ? __ldg(p.bias + m) : 0.f;
-  float rs = 1.f;
-  if constexpr (KIND == KIND_F16) rs = (m < p.M) ? __ldg(p.row_scale + m) : 0.f;
+  const float bias = t.bias;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int n0 = nb * p.Nt + half * ntw + c * 32;
     if (c * 32 < ntw && n0 < p.N) {
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = acc[c * 32 + j];
-        if constexpr (KIND == KIND_F16) x = x * rs * scale_down(scale_exp((n0 + j < p.N) ? __ldg(p.colmax + n0 + j) : 0u));
-        x += bias;
-        v[j] = relu ? fmaxf(x, 0.f) : x;
-      }
       if (ct) {  // C^T [N, M]: a register is one n, the 32 lanes are 32 consecutive m -> coalesced
-        if (m < p.M) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) p.C[(long long)(n0 + j) * p.ldc + m] = v[j];
+        for (int j = 0; j < 32; ++j) {
+          float x = acc[c * 32 + j];
+          if constexpr (KIND == KIND_F16) x = x * rs * __shfl_sync(0xffffffffu, t.cs[c], j);
+          x += bias;
+          x = relu ? fmaxf(x, 0.f) : x;
+          if (m < p.M && n0 + j < p.N) p.C[(long long)(n0 + j) * p.ldc + m] = x;
         }
-      } else if (m < p.M) {
-        float* dst = p.C + (long long)m * p.ldc + n0;
-        if (vec4 && n0 + 32 <= p.N) {
+      } else {   // C [M, N]: through the transposer, one 128-byte row segment per store instruction
+        const int n = n0 + lane;
+        const float cs = t.cs[c];
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            __stcs(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) dst[j] = v[j];
+        for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = acc[c * 32 + j] * rs;
+        __syncwarp();
+        float* dst = p.C + (long long)m0 * p.ldc + n;
+        const int rows = (n < p.N) ? p.M - m0 : 0;  // rows of this warp's block that exist (this lane's column too)
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          float x = stg[r * STG_LD + lane] * cs;
+          x += __shfl_sync(0xffffffffu, bias, r);
+          x = relu ? fmaxf(x, 0.f) : x;
+          if (r < rows) __stcs(dst + (long long)r * p.ldc, x);
         }
       }
     }
@@ -763,11 +824,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
     const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
     const int ntw = p.Nt >> 1;            // columns per warp (multiple of 32, <= 128)
+    float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256) + (warp - 2) * (32 * STG_LD);
     uint32_t g = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       const int mb = tile / p.NB, nb = tile % p.NB;
       const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
+      if constexpr (SDDMM) {
+        if (t1 - t0 <= p.chunk && !(p.terms & 8)) {
+          // short contraction (one chunk): nothing to add up, so every group goes TMEM -> transposer -> pattern entries
+          // without the 128 accumulator registers: the store loop gets them for 32 iterations in flight
+          const int as = (int)(g & 1u);
+          ok = mbar_wait_bounded(acc_full + as, (g >> 1) & 1u, p.ctl + 1, 400 + as);
+          if (!ok) break;
+          tc_fence_after();
+          TilePre pre;
+          tc_tile_prefetch<KIND, true>(p, mb, nb, q, half, ntw, lane, pre);
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.Nt + half * ntw);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 < ntw) {
+              uint32_t v[32];
+              tmem_ld32(t_addr + (uint32_t)(c * 32), v);
+              tmem_ld_wait();
+              if ((c + 1) * 32 >= ntw) {  // last group read: hand the TMEM buffer back before the stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + as);
+              }
+              const int grp = (nb * p.Nt + half * ntw + c * 32) >> 5;
+              if (grp < p.groups) {
+                float vf[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vf[j] = __uint_as_float(v[j]);
+                tc_sddmm_group_store<32>(p.C, vf, pre.rs, pre.cs[c], pre.msk[c], pre.bs[c], lane, stg);
+              }
+            }
+          }
+          ++g;
+          continue;
+        }
+      }
       float acc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -792,7 +889,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
         if (lane == 0) mbar_arrive(acc_empty + as);  // this warp's part of the buffer is drained
       }
       if (!ok) break;
-      if (!(p.terms & 8)) tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane);
+      if (!(p.terms & 8)) {
+        // (fetching these before the accumulator wait was measured slower: 14 more live registers spill in the drain)
+        TilePre pre;
+        tc_tile_prefetch<KIND, SDDMM>(p, mb, nb, q, half, ntw, lane, pre);
+        tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane, stg, pre);
+      }
     }
   }
   tc_fence_before();
@@ -1028,6 +1130,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_sp
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int ntw = p.Nt >> 1;
+    float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256) + (warp - 2) * (32 * STG_LD);
     uint32_t g = 0;
     bool ok = true;
     for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
@@ -1058,7 +1161,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_sp
         if (lane == 0) mbar_arrive_remote(acc_empty + as, 0);  // the leader's barrier collects both CTAs
       }
       if (!ok) break;
-      if (mb < p.MB && !(p.terms & 8)) tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane);
+      if (mb < p.MB && !(p.terms & 8)) {
+        TilePre pre;
+        tc_tile_prefetch<KIND, SDDMM>(p, mb, nb, q, half, ntw, lane, pre);
+        tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane, stg, pre);
+      }
     }
   }
   tc_fence_before();
@@ -1316,8 +1423,8 @@ static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
   // CTA pairs (cta_group::2) when there are at least two row blocks: each CTA stages A + half of the B tile
   if (options().tc_pair != 0 && p.MB >= 2 && p.pair_ptr_ok) {
     const int stage2 = A_TILE + p.Nt * 128;
-    p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage2));
-    const size_t smem2 = (size_t)p.stages * stage2 + 1024 + 256;
+    p.stages = std::min(MAX_STAGES, (int)((TC_SMEM_MAX - 1024 - 256 - STG_BYTES) / stage2));
+    const size_t smem2 = (size_t)p.stages * stage2 + 1024 + 256 + STG_BYTES;
     const int cap = tc_pair_capacity<KIND, SDDMM>(smem2);
     g_tc_pair_capacity = cap;
     if (cap > 0) {
@@ -1329,8 +1436,8 @@ static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
     }
   }
   const int stage_bytes = A_TILE + p.Nt * 256;
-  p.stages = std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  p.stages = std::min(MAX_STAGES, (int)((TC_SMEM_MAX - 1024 - 256 - STG_BYTES) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + STG_BYTES;  // ring | barriers | transposers
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CUDA_OK(cudaGetDevice(&dev));
