@@ -715,6 +715,10 @@ def run_ours(args):
     sh_bytes = 4 * (r1 - r0 + 1) + 8 * (p1 - p0) + 4 * K * N + 4 * (r1 - r0) * N
     k_ms = kern_ms / args.steps
     achieved = sh_bytes / (k_ms * 1e-3) / 1e9
+    # SURVEY 8(d)'s formula charges all K rows of B to the launch; a shard (and an R-MAT with empty columns) touches
+    # fewer: the same figure with only the distinct B rows this rank's non-zeros name, reported beside it
+    b_rows_touched = int(torch.unique(col).numel()) if col.numel() else 0
+    sh_bytes_touched = sh_bytes - 4 * (K - b_rows_touched) * N
     out = {
         "metric": "CSR SpMM forward GFLOP/s (2*nnz*N)", "value": round(flops(w) / (ms_per_step * 1e-3) / 1e9, 2),
         "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -734,6 +738,9 @@ def run_ours(args):
                      "kernel": "spmm_flat_kernel (single launch: split rows are summed by the last arriving task)",
                      "kernel_ms": round(k_ms, 5), "kernel_ms_per_rank": [round(x, 5) for x in per_rank_ms],
                      "algorithmic_bytes": sh_bytes,
+                     "b_rows_touched": b_rows_touched, "algorithmic_bytes_touched_rows_of_B_only": sh_bytes_touched,
+                     "frac_touched_rows_of_B_only": round(sh_bytes_touched / (k_ms * 1e-3) / 1e9 / peak, 4),
+                     "scope": "rank 0's launch over its own shard against ONE GPU's peak",
                      "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
         "e2e": {"value": round(flops(w) / (e2e_ms * 1e-3) / 1e9, 2), "unit": "GFLOP/s",
                 "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": int(M * N * 4),
