@@ -294,6 +294,7 @@ int b200_smoke_kernel(void* stream, int* sm_count) {
   return B200_OK;
 }
 
+static int g_trace_idx = 0;  // debug timeline cursor (tc_trace_idx / tc_trace_word)
 int b200_set_option(const char* name, int64_t value) {
   B200_REQUIRE(name != nullptr, "option name");
   if (!strcmp(name, "stage_mode")) { options().stage_mode = (int)value; return B200_OK; }
@@ -315,7 +316,9 @@ int b200_set_option(const char* name, int64_t value) {
     B200_REQUIRE(value == 0 || (value % 64 == 0 && value >= 64 && value <= 256), "tc_nt must be 0 or a multiple of 64 up to 256");
     options().tc_nt = (int)value; return B200_OK;
   }
-  if (!strcmp(name, "tc_terms")) { options().tc_terms = (int)value & 63;  /* bits 3-5: timing studies (skip store / B copy / A copy) */ return B200_OK; }
+  if (!strcmp(name, "tc_terms")) { options().tc_terms = (int)value & 1023;  /* bits 3-5: timing studies (skip store / B copy / A copy); bits 6-8: SDDMM epilogue studies; bit 9: timeline of CTA 0 */ return B200_OK; }
+  if (!strcmp(name, "tc_trace_sync")) { return (value ? b200::tc_trace_sync() : b200::tc_trace_clear()) == 0 ? B200_OK : B200_ERR_CUDA; }
+  if (!strcmp(name, "tc_trace_idx")) { g_trace_idx = (int)value; return B200_OK; }
   if (!strcmp(name, "tc_chunk")) { options().tc_chunk = (int)std::max<int64_t>(1, value); return B200_OK; }
   if (!strcmp(name, "tc_kind")) { options().tc_kind = value ? 1 : 0; return B200_OK; }
   if (!strcmp(name, "tc_pair")) { options().tc_pair = value ? 1 : 0; return B200_OK; }
@@ -326,6 +329,7 @@ int b200_set_option(const char* name, int64_t value) {
 int64_t b200_get_option(const char* name) {
   if (!name) return -1;
   if (!strcmp(name, "tc_last_kernel")) return b200::g_tc_last_kernel;
+  if (!strcmp(name, "tc_trace_word")) return b200::tc_trace_word(g_trace_idx++);
   if (!strcmp(name, "tc_pair_capacity")) return b200::g_tc_pair_capacity;
   if (!strcmp(name, "stage_mode")) return options().stage_mode;
   if (!strcmp(name, "items_per_task")) return options().items_per_task;

@@ -359,6 +359,9 @@ int slab_store_refresh(const int* col, const float* val, SlabStore* st, cudaStre
 void slab_store_free(SlabStore* st);
 int launch_spmm_slab(const SlabStore& st, const int* col, const float* val, const float* B, float* C, long long ldc,
                      const float* bias, int relu, cudaStream_t s);
+int tc_trace_sync();
+int tc_trace_clear();
+long long tc_trace_word(int i);
 extern int g_tc_last_kernel, g_tc_pair_capacity;  // diagnostics of the last tensor-core launch (tc_gemm.cu)
 // pattern of a CSR matrix for the tensor-core SDDMM's sampling epilogue
 struct TcSample {

@@ -581,6 +581,20 @@ constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int TC_SMEM_MAX = 227 * 1024;
 
+// Debug timeline (tc_terms bit 9): CTA 0's producer lane, MMA lane and first epilogue warp record (code, globaltimer)
+// pairs into three regions of a device buffer; read back through b200_set_option("tc_trace_sync") / get_option.
+constexpr int TRACE_REGION = 2048;  // words per role
+__device__ unsigned long long g_tc_trace[3 * TRACE_REGION];
+__device__ __forceinline__ void tc_trace(bool on, int role, int& n, int code) {
+  if (on && n + 2 <= TRACE_REGION) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_tc_trace[role * TRACE_REGION + n] = (unsigned long long)code;
+    g_tc_trace[role * TRACE_REGION + n + 1] = t;
+    n += 2;
+  }
+}
+
 // What the final step of a tile needs from global memory, fetched in one batch (one round trip, not one per group).
 // Lane = row m for rs / bias / msk / bs; lane = column (of the c-th 32-column group) for cs.
 struct TilePre {
@@ -647,9 +661,43 @@ __device__ __forceinline__ void tc_sddmm_group_store(float* __restrict__ out, co
   }
 }
 
+// Rows of a filled transposer -> C: lane = column, one 128-byte row segment per store.  Four rows per step, loads
+// first, the row pointer carried in a register pair the compiler may not rematerialise (left to itself it emitted a
+// branch, a 64-bit multiply and a constant reload per row and serialised the rows: 128 cycles each, measured with
+// the timeline of tools/tc_trace.py).  The pad word of a row carries its bias.
+template <bool RELU, bool FULL>
+__device__ __forceinline__ void tc_store_rows(const float* __restrict__ stg, int lane, float cs, float* dst,
+                                              long long ldc, int rows) {
+  const long long step = ldc * (long long)sizeof(float);
+  unsigned long long a = reinterpret_cast<unsigned long long>(dst);
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 4) {
+    float x[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[k] = stg[(r0 + k) * STG_LD + lane];
+      b[k] = stg[(r0 + k) * STG_LD + 32];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float y = x[k] * cs + b[k];
+      if (RELU) y = fmaxf(y, 0.f);
+      if (FULL) {
+        asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(a), "f"(y) : "memory");
+      } else {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %2, %3;\n\t@q st.global.cs.f32 [%0], %1;\n\t}"
+                     ::"l"(a), "f"(y), "r"(r0 + k), "r"(rows) : "memory");
+      }
+      a += (unsigned long long)step;
+      asm volatile("" : "+l"(a));
+    }
+  }
+}
+
 template <int KIND, bool SDDMM>
 __device__ __forceinline__ void tc_tile_store(const TcParams& p, const float (&acc)[128], int mb, int nb, int q, int half,
-                                          int ntw, int lane, float* __restrict__ stg, const TilePre& t) {
+                                          int ntw, int lane, float* __restrict__ stg, const TilePre& t,
+                                          bool tr = false, int* trn = nullptr) {
   const bool relu = (p.flags & 4u) != 0, ct = (p.flags & 2u) != 0;
   const int m0 = mb * BM + q * 32;
   const int m = m0 + lane;
@@ -686,16 +734,20 @@ __device__ __forceinline__ void tc_tile_store(const TcParams& p, const float (&a
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = acc[c * 32 + j] * rs;
+        stg[lane * STG_LD + 32] = bias;  // the pad word of the row carries its bias
         __syncwarp();
+        if (tr) tc_trace(true, 2, *trn, 30 + c);  // transposer filled
         float* dst = p.C + (long long)m0 * p.ldc + n;
-        const int rows = (n < p.N) ? p.M - m0 : 0;  // rows of this warp's block that exist (this lane's column too)
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          float x = stg[r * STG_LD + lane] * cs;
-          x += __shfl_sync(0xffffffffu, bias, r);
-          x = relu ? fmaxf(x, 0.f) : x;
-          if (r < rows) __stcs(dst + (long long)r * p.ldc, x);
+        const int rows = (n < p.N) ? min(p.M - m0, 32) : 0;  // rows of this warp's block that exist (for this lane's column)
+        const bool full = __all_sync(0xffffffffu, rows == 32);
+        if (full) {
+          if (relu) tc_store_rows<true, true>(stg, lane, cs, dst, p.ldc, 32);
+          else tc_store_rows<false, true>(stg, lane, cs, dst, p.ldc, 32);
+        } else {
+          if (relu) tc_store_rows<true, false>(stg, lane, cs, dst, p.ldc, rows);
+          else tc_store_rows<false, false>(stg, lane, cs, dst, p.ldc, rows);
         }
+        if (tr) tc_trace(true, 2, *trn, 40 + c);  // group written
       }
     }
   }
@@ -758,12 +810,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      const bool tr = (p.terms & 512) && blockIdx.x == 0;
+      int trn = 0;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int mb = tile / p.NB, nb = tile % p.NB;
         const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
         for (int t = t0; t < t1; ++t) {
+          tc_trace(tr, 0, trn, 1);  // producer: starts waiting for the slot
           ok = mbar_wait_bounded(empty + stage, phase ^ 1u, p.ctl + 1, 100 + stage);
           if (!ok) break;
+          tc_trace(tr, 0, trn, 2);  // producer: slot free, copies issued next
           const int kt = SDDMM ? t : __ldg(p.blk_kt + t);
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
           const bool cp_a = !(p.terms & 32), cp_b = !(p.terms & 16);  // (timing studies: skip a copy)
@@ -787,20 +843,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       uint32_t phase = 0;
       uint32_t g = 0;  // chunks issued so far: TMEM buffer g & 1, its barrier phase (g >> 1) & 1
       bool ok = true;
+      const bool tr = (p.terms & 512) && blockIdx.x == 0;
+      int trn = 0;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int mb = tile / p.NB;
         const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
         for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
           const int as = (int)(g & 1u);
+          tc_trace(tr, 1, trn, 10);  // MMA lane: starts waiting for a free accumulator
           ok = mbar_wait_bounded(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as);
           if (!ok) break;
+          tc_trace(tr, 1, trn, 11);  // accumulator free
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(as * p.Nt);
           uint32_t acc = 0;
           const int c1 = min(c0 + p.chunk, t1);
           for (int t = c0; t < c1; ++t) {
+            tc_trace(tr, 1, trn, 12);  // MMA lane: starts waiting for operands
             ok = mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage);
             if (!ok) break;
+            tc_trace(tr, 1, trn, 13);  // operands landed
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + A_TILE;
@@ -827,6 +889,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
     float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256) + (warp - 2) * (32 * STG_LD);
     uint32_t g = 0;
     bool ok = true;
+    const bool etr = (p.terms & 512) && blockIdx.x == 0 && warp == 2 && lane == 0;
+    int etrn = 0;
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       const int mb = tile / p.NB, nb = tile % p.NB;
       const int t0 = SDDMM ? 0 : __ldg(p.blk_ptr + mb), t1 = SDDMM ? p.KT : __ldg(p.blk_ptr + mb + 1);
@@ -870,8 +934,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       for (int j = 0; j < 128; ++j) acc[j] = 0.f;
       for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
         const int as = (int)(g & 1u);
+        tc_trace(etr, 2, etrn, 20);  // epilogue: starts waiting for a chunk's sums
         ok = mbar_wait_bounded(acc_full + as, (g >> 1) & 1u, p.ctl + 1, 400 + as);
         if (!ok) break;
+        tc_trace(etr, 2, etrn, 21);  // sums complete, drain starts
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.Nt + half * ntw);
 #pragma unroll
@@ -887,14 +953,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + as);  // this warp's part of the buffer is drained
+        tc_trace(etr, 2, etrn, 22);  // drained
       }
       if (!ok) break;
+      tc_trace(etr, 2, etrn, 23);  // tile store starts
       if (!(p.terms & 8)) {
         // (fetching these before the accumulator wait was measured slower: 14 more live registers spill in the drain)
         TilePre pre;
         tc_tile_prefetch<KIND, SDDMM>(p, mb, nb, q, half, ntw, lane, pre);
-        tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane, stg, pre);
+        tc_trace(etr, 2, etrn, 25);  // scales / bias fetched
+        tc_tile_store<KIND, SDDMM>(p, acc, mb, nb, q, half, ntw, lane, stg, pre, etr, &etrn);
       }
+      tc_trace(etr, 2, etrn, 24);  // tile stored
     }
   }
   tc_fence_before();
@@ -1384,6 +1454,17 @@ static int tc_pack_operand(const float* X, long long ld, int rows, int depth, bo
   B200_LAUNCH_OK("tc_pack_b_kernel");
   return B200_OK;
 }
+
+// debug timeline read-back (tools/tc_trace.py)
+static unsigned long long g_tc_trace_host[3 * TRACE_REGION];
+int tc_trace_sync() {
+  return cudaMemcpyFromSymbol(g_tc_trace_host, g_tc_trace, sizeof(g_tc_trace_host)) == cudaSuccess ? 0 : -1;
+}
+int tc_trace_clear() {
+  memset(g_tc_trace_host, 0, sizeof(g_tc_trace_host));
+  return cudaMemcpyToSymbol(g_tc_trace, g_tc_trace_host, sizeof(g_tc_trace_host)) == cudaSuccess ? 0 : -1;
+}
+long long tc_trace_word(int i) { return (i >= 0 && i < 3 * TRACE_REGION) ? (long long)g_tc_trace_host[i] : -1; }
 
 int g_tc_last_kernel = 0;    // 1 = one CTA per tile, 2 = CTA pairs (diagnostics: b200_get_option("tc_last_kernel"))
 int g_tc_pair_capacity = -1; // co-resident CTA pairs reported by the occupancy query
