@@ -181,7 +181,16 @@ tc_colmax_kernel(const float* __restrict__ B, long long ld, int K, int N, uint32
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     uint32_t mx = 0;
-    for (int k = blockIdx.y; k < K; k += gridDim.y) mx = max(mx, __float_as_uint(__ldg(B + (long long)k * ld + n)) & 0x7fffffffu);
+    for (int k = blockIdx.y; k < K; k += 8 * gridDim.y) {  // eight independent loads in flight per thread
+      uint32_t v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kk = k + i * (int)gridDim.y;
+        v[i] = (kk < K) ? __float_as_uint(__ldg(B + (long long)kk * ld + n)) & 0x7fffffffu : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = max(mx, v[i]);
+    }
     if (mx >= 0x7f800000u) { atomicOr(nonfinite, 1); mx = 0; }
     atomicMax(colmax + n, mx);
   } else {
