@@ -689,10 +689,12 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
   const double t_mma = 6.0 * (double)(MB * 128) * (double)K * n_pad / (f16 ? 1.3e9 : 0.65e9);
   if (sddmm) {
     // grad of the values: every output tile of the M x K product is computed and sampled, so the tile count (not the
-    // contraction length N) dominates: 30 us + M_pad * K / 4.5e5 + MMAs; the gather SDDMM runs at ~3.3e6 nnz*N per us
-    // (1.25e6 below 24 columns)
+    // contraction length N) dominates.  Measured with the transposer epilogue (profiles/r2_configs.md, 16384^2):
+    // 0.37 / 0.37 / 0.43 ms at N = 16 / 64 / 256 for 50 % and 90 % sparsity alike -> 30 us + M_pad * K / 9.0e5 for the
+    // sampled stores + 0.4 x the MMAs (they overlap the store phase of the previous tile); the gather SDDMM runs at
+    // ~3.3e6 nnz*N per us (1.25e6 below 24 columns)
     const double t_g = 12.0 + (double)p->nnz * (double)N / (N < 24 ? 1.25e6 : 3.3e6);
-    const double t_t = 30.0 + (double)(MB * 128) * (double)K / 4.5e5 + t_mma;
+    const double t_t = 30.0 + (double)(MB * 128) * (double)K / 9.0e5 + 0.4 * t_mma;
     return t_t < t_g;
   }
   const double t_tc = 28.0 + std::max(t_stream, t_mma);

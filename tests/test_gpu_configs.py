@@ -96,6 +96,32 @@ def test_config5_sweep_points(c5_matrices, sparsity, N):
     plan.close()
 
 
+@pytest.mark.parametrize("sparsity,N", [(0.9, 64), (0.99, 64)])
+def test_config5_backward_points(c5_matrices, sparsity, N):
+    """grad_B over the cached transpose and grad_A (SDDMM on the pattern) at the sweep's own size, on whatever path the
+    plan's cost models pick (90 % sparse x 64: tiles for both; 99 %: gather kernels)."""
+    import torch
+    M = K = 16384
+    rp, ci, va = c5_matrices(sparsity)
+    B = synthetic.dense_operand(K, N, seed=1, signed=True)
+    G = synthetic.dense_operand(M, N, seed=2, signed=True)
+    crow, col, val, Bd, Gd = _dev(rp, ci, va, B, G)
+    plan = capi.Plan(crow, col, val, (M, K))
+    dB = plan.backward_B(Gd, torch.empty(K, N, device="cuda:0"))
+    dA = plan.backward_A_ex(Gd, Bd, torch.empty(len(va), device="cuda:0"))
+    torch.cuda.synchronize()
+    assert plan.tc_timeout() == 0
+    assert plan.tc_info()["last_path"] == (1 if plan.would_use_tc(N, side=2) else 0)
+    assert oracle.rel_err(dB.cpu().numpy(), oracle.spmm_t_f64(rp, ci, va, (M, K), G)) <= TOL
+    assert oracle.rel_err(dA.cpu().numpy(), oracle.sddmm_f64(rp, ci, (M, K), G, B)) <= TOL
+    # the other SDDMM path on the same operands agrees too
+    dA2 = plan.backward_A_ex(Gd, Bd, torch.empty(len(va), device="cuda:0"), flags=OP_NO_TC)
+    torch.cuda.synchronize()
+    assert plan.tc_info()["last_path"] == 0
+    assert oracle.rel_err(dA2.cpu().numpy(), dA.cpu().numpy().astype(np.float64)) <= 2 * TOL
+    plan.close()
+
+
 def test_config4_rmat_scale20_split_rows_and_sample():
     import torch
     rp, ci, va, shape = synthetic.rmat_csr(scale=20, edge_factor=16, seed=0)
