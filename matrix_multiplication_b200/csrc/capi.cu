@@ -322,6 +322,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_chunk")) { options().tc_chunk = (int)std::max<int64_t>(1, value); return B200_OK; }
   if (!strcmp(name, "tc_kind")) { options().tc_kind = value ? 1 : 0; return B200_OK; }
   if (!strcmp(name, "tc_pair")) { options().tc_pair = value ? 1 : 0; return B200_OK; }
+  if (!strcmp(name, "tc_sddmm_short")) { options().tc_sddmm_short = value ? 1 : 0; return B200_OK; }
   if (!strcmp(name, "tc_min_density_pct")) { options().tc_min_density_pct = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
   return B200_ERR_INVALID;
@@ -348,6 +349,7 @@ int64_t b200_get_option(const char* name) {
   if (!strcmp(name, "tc_chunk")) return options().tc_chunk;
   if (!strcmp(name, "tc_kind")) return options().tc_kind;
   if (!strcmp(name, "tc_pair")) return options().tc_pair;
+  if (!strcmp(name, "tc_sddmm_short")) return options().tc_sddmm_short;
   if (!strcmp(name, "tc_min_density_pct")) return options().tc_min_density_pct;
   return -1;
 }

@@ -985,6 +985,202 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
   tc_exit_ticket(p.ctl);
 }
 
+// ---- SDDMM, short contractions: transposed product, 16 epilogue warps ----------------------------------------------
+// When the whole contraction fits one TMEM accumulation (KT <= chunk: every N of config 5), a tile's time is its
+// sampled stores, and in tc_spmm_kernel those are bound by the LSU / MIO instruction rate: per 32 x 32 group 33 STS +
+// 64 LDS + 32 SHFL + 32 STG through the transposer (ncu: mio_throttle is the first stall reason, LSU pipe 59 %).
+// This variant computes D^T instead: the packed B block (128 pattern COLUMNS) is the MMA's M operand and the packed
+// G block (128 pattern ROWS) its N operand — both operands have the same packed layout, so this is a swap of two
+// pointers.  A TMEM lane is then a pattern column and a register a pattern row: exactly what the row-wise store needs
+// (the lanes of one instruction hold 32 consecutive columns of one row), with NO transposer.  Per group: one STS.128
+// (each lane publishes mask / offset / scale of its row), then per row one broadcast LDS.128 and one STG.
+// 16 epilogue warps (no accumulator registers needed: 64 registers per thread), tiles of 128 x 128, warp w owns the
+// group (TMEM lane quarter w % 4 = 32 columns, register block (w - 2) / 4 = 32 rows), four TMEM buffers, three 64 KB
+// operand stages; pattern words and scales of the NEXT tile are fetched before the wait for the current one.
+constexpr int SH_EPI_WARPS = 16;
+constexpr int SH_THREADS = (2 + SH_EPI_WARPS) * 32;
+constexpr int SH_NT = 128;
+constexpr int SH_STAGES = 3;
+constexpr int SH_STAGE_BYTES = A_TILE + SH_NT * 256;
+constexpr int SH_BUFS = 512 / SH_NT;
+constexpr int SH_SIDE_BYTES = 32 * 16;  // per warp: (mask, offset, row scale, -) of its 32 rows
+constexpr size_t SH_SMEM = (size_t)SH_STAGES * SH_STAGE_BYTES + 1024 + 256 + (size_t)SH_EPI_WARPS * SH_SIDE_BYTES;
+
+struct GroupPre {
+  float rs, cs;   // scale of this lane's ROW (lane = row while fetching) / of this lane's COLUMN
+  uint32_t msk;   // pattern bits of (row = lane, the group's 32 columns)
+  int bs;         // position of that row's first entry of the group in the CSR value array
+};
+
+// q: which 32 columns of the tile's 128 (TMEM lane quarter), rb: which 32 rows
+template <int KIND>
+__device__ __forceinline__ GroupPre tc_group_prefetch(const TcParams& p, int tile, int q, int rb, int lane) {
+  const int mb = tile / p.NB, nb = tile % p.NB;
+  const int m = mb * BM + rb * 32 + lane;
+  const int grp = nb * (BM / 32) + q;
+  GroupPre t;
+  t.rs = 1.f; t.cs = 1.f; t.msk = 0u; t.bs = 0;
+  if (grp < p.groups) {
+    if constexpr (KIND == KIND_F16) t.cs = scale_down(scale_exp(__ldg(p.colmax + grp * 32 + lane)));
+    if (m < p.M) {
+      t.msk = __ldg(p.samp_mask + (size_t)grp * p.M + m);
+      t.bs = __ldg(p.samp_off + (size_t)grp * p.M + m);
+      if constexpr (KIND == KIND_F16) t.rs = scale_down(scale_exp(__ldg(p.amax + m)));
+    }
+  }
+  return t;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(SH_THREADS, 1) tc_sddmm_short_kernel(const TcParams p) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  if (*reinterpret_cast<const volatile int*>(p.ctl) != 0) {  // Inf / NaN in a dense operand (uniform over the grid)
+    csr_order_sddmm(p.row_ptr, p.col, p.M, p.N, p.G, p.g_sm, p.g_sn, p.B, p.b_sk, p.b_sn, p.C);
+    tc_exit_ticket(p.ctl);
+    return;
+  }
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  unsigned char* smem = tc_smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)SH_STAGES * SH_STAGE_BYTES);
+  uint64_t* empty = full + SH_STAGES;
+  uint64_t* acc_full = empty + SH_STAGES;
+  uint64_t* acc_empty = acc_full + SH_BUFS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SH_BUFS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SH_STAGES; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < SH_BUFS; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, SH_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const int n_tiles = p.MB * p.NB;  // tile = (block of 128 pattern rows mb, block of 128 pattern columns nb)
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: M operand = 128 packed rows of B (pattern columns), N operand = 128 of G =====
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        const int mb = tile / p.NB, nb = tile % p.NB;
+        for (int kt = 0; kt < p.KT; ++kt) {
+          ok = mbar_wait_bounded(empty + stage, phase ^ 1u, p.ctl + 1, 100 + stage);
+          if (!ok) break;
+          unsigned char* sa = smem + (size_t)stage * SH_STAGE_BYTES;
+          mbar_expect_tx(full + stage, (uint32_t)SH_STAGE_BYTES);
+          tma_bulk_g2s(sa, p.b_pack + ((size_t)kt * p.NG + (size_t)nb * (BM / 8)) * ATOM, A_TILE, full + stage);
+          tma_bulk_g2s(sa + A_TILE, p.a_tiles + ((size_t)kt * p.NGa + (size_t)mb * (SH_NT / 8)) * ATOM,
+                       (uint32_t)SH_NT * 256u, full + stage);
+          if (++stage == SH_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: the whole contraction of a tile goes into one TMEM buffer =====
+      const uint32_t idesc = umma_idesc(KIND, SH_NT);
+      int stage = 0;
+      uint32_t phase = 0, g = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++g) {
+        const uint32_t as = g % SH_BUFS;
+        ok = mbar_wait_bounded(acc_empty + as, ((g / SH_BUFS) & 1u) ^ 1u, p.ctl + 1, 200 + (int)as);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d = tmem_base + as * SH_NT;
+        uint32_t acc = 0;
+        for (int kt = 0; kt < p.KT; ++kt) {
+          ok = mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * SH_STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
+            const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
+            if (p.terms & 2) { umma<KIND>(d, a_hi, b_lo, idesc, acc); acc = 1; }
+            if (p.terms & 4) { umma<KIND>(d, a_lo, b_hi, idesc, acc); acc = 1; }
+            if (p.terms & 1) { umma<KIND>(d, a_hi, b_hi, idesc, acc); acc = 1; }
+          }
+          umma_commit(empty + stage);
+          if (++stage == SH_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(acc_full + as);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..17: one 32 x 32 group of every tile, TMEM -> registers -> entries on A's pattern =====
+    const int q = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp id % 4): 32 columns
+    const int rb = (warp - 2) >> 2;  // which 32 rows of the tile (TMEM columns)
+    uint4* side = reinterpret_cast<uint4*>(smem + (size_t)SH_STAGES * SH_STAGE_BYTES + 256) + (warp - 2) * 32;
+    const uint32_t lbit = 1u << lane, lt = lbit - 1u;
+    const uint32_t side_a = smem_u32(side);
+    unsigned long long outp = reinterpret_cast<unsigned long long>(p.C);
+    asm volatile("" : "+l"(outp));  // (kept in a register pair: no constant reload per row)
+    uint32_t g = 0;
+    bool ok = true;
+    int tile = blockIdx.x;
+    GroupPre nxt{1.f, 1.f, 0u, 0};
+    if (tile < n_tiles) nxt = tc_group_prefetch<KIND>(p, tile, q, rb, lane);
+    for (; tile < n_tiles && ok; tile += gridDim.x, ++g) {
+      const GroupPre cur = nxt;
+      if (tile + (int)gridDim.x < n_tiles) nxt = tc_group_prefetch<KIND>(p, tile + (int)gridDim.x, q, rb, lane);
+      const uint32_t as = g % SH_BUFS;
+      ok = mbar_wait_bounded(acc_full + as, (g / SH_BUFS) & 1u, p.ctl + 1, 400 + (int)as);
+      if (!ok) break;
+      tc_fence_after();
+      uint32_t v[32];  // v[j] = D^T(column of this lane, row rb * 32 + j)
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * SH_NT + (uint32_t)(rb * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + as);  // the buffer goes back before the stores
+      if (!__any_sync(0xffffffffu, cur.msk != 0u)) continue;  // (also: group beyond K, rows beyond M)
+      side[lane] = make_uint4(cur.msk, (uint32_t)cur.bs, __float_as_uint(cur.rs), 0u);
+      __syncwarp();
+      const float cs = cur.cs;
+      // hand-structured (left to itself the compiler emitted a branch, three scalar LDS and a reload of the output
+      // pointer per row): one broadcast LDS.128 per row, straight-line ALU work, one predicated STG
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        uint32_t mk, bs, sc, pad;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(mk), "=r"(bs), "=r"(sc), "=r"(pad)
+                     : "r"(side_a + (uint32_t)j * 16u));
+        const float x = __uint_as_float(v[j]) * cs * __uint_as_float(sc);
+        const int idx = (int)bs + __popc(mk & lt);
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t.reg .b64 a;\n\t"
+            "and.b32 t, %0, %1;\n\t"
+            "setp.ne.u32 q, t, 0;\n\t"
+            "mad.wide.s32 a, %2, 4, %3;\n\t"
+            "@q st.global.f32 [a], %4;\n\t}"
+            ::"r"(mk), "r"(lbit), "r"(idx), "l"(outp), "f"(x)
+            : "memory");
+      }
+      __syncwarp();  // everybody has read `side` before the next tile overwrites it
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  tc_exit_ticket(p.ctl);
+}
+
 // ---- CTA-pair variant: tcgen05.mma.cta_group::2 ------------------------------------------------------------------
 // Two CTAs of a cluster (one TPC) multiply a 256 x Nt tile together: each holds its own 128 rows of A and HALF of
 // the B tile (Nt / 2 columns), the tensor cores of both SMs read both halves, each SM's TMEM receives its 128 rows of
@@ -1510,6 +1706,27 @@ template <int KIND, bool SDDMM>
 static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
   p.chunk = std::max(1, options().tc_chunk);
   p.terms = options().tc_terms;
+  if constexpr (SDDMM) {
+    // short contraction: the 16-epilogue-warp kernel over 128 x 128 tiles (the packed operands are laid out in
+    // groups of 8 rows, so the tile width is free to differ from the nt they were padded for)
+    if (options().tc_sddmm_short != 0 && p.KT <= p.chunk && (p.terms & ~7) == 0 && p.Nt % SH_NT == 0) {
+      static bool attr_short[64] = {false};
+      int dev = 0;
+      B200_CUDA_OK(cudaGetDevice(&dev));
+      if (!attr_short[dev & 63]) {
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_sddmm_short_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)SH_SMEM));
+        attr_short[dev & 63] = true;
+      }
+      p.NB = p.NB * (p.Nt / SH_NT);
+      p.Nt = SH_NT;
+      const int grid = std::max(1, std::min(device_sm_count(), p.MB * p.NB));
+      g_tc_last_kernel = 3;
+      tc_sddmm_short_kernel<KIND><<<grid, SH_THREADS, SH_SMEM, s>>>(p);
+      B200_LAUNCH_OK("tc_sddmm_short_kernel");
+      return B200_OK;
+    }
+  }
   // CTA pairs (cta_group::2) when there are at least two row blocks: each CTA stages A + half of the B tile
   if (options().tc_pair != 0 && p.MB >= 2 && p.pair_ptr_ok) {
     const int stage2 = A_TILE + p.Nt * 128;
