@@ -322,7 +322,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_chunk")) { options().tc_chunk = (int)std::max<int64_t>(1, value); return B200_OK; }
   if (!strcmp(name, "tc_kind")) { options().tc_kind = value ? 1 : 0; return B200_OK; }
   if (!strcmp(name, "tc_pair")) { options().tc_pair = value ? 1 : 0; return B200_OK; }
-  if (!strcmp(name, "tc_sddmm_short")) { options().tc_sddmm_short = value ? 1 : 0; return B200_OK; }
+  if (!strcmp(name, "tc_sddmm_short")) { options().tc_sddmm_short = (int)(value & 3); return B200_OK; }
   if (!strcmp(name, "tc_min_density_pct")) { options().tc_min_density_pct = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);
   return B200_ERR_INVALID;
@@ -691,12 +691,12 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
   const double t_mma = 6.0 * (double)(MB * 128) * (double)K * n_pad / (f16 ? 1.3e9 : 0.65e9);
   if (sddmm) {
     // grad of the values: every output tile of the M x K product is computed and sampled, so the tile count (not the
-    // contraction length N) dominates.  Measured with the transposer epilogue (profiles/r2_configs.md, 16384^2):
-    // 0.37 / 0.37 / 0.43 ms at N = 16 / 64 / 256 for 50 % and 90 % sparsity alike -> 30 us + M_pad * K / 9.0e5 for the
-    // sampled stores + 0.4 x the MMAs (they overlap the store phase of the previous tile); the gather SDDMM runs at
-    // ~3.3e6 nnz*N per us (1.25e6 below 24 columns)
+    // contraction length N) dominates.  Measured on 16384^2 with the transposed-product kernel (profiles/
+    // r2_sddmm_short_probe.txt): 0.20 / 0.20 / 0.23 / 0.31 ms at N = 16 / 64 / 128 / 256 and 90 % sparsity (0.23 / 0.24 /
+    // 0.25 / 0.37 at 50 %) -> 30 us + M_pad * K / 1.7e6 for the sampled stores + 0.45 x the MMAs (they overlap the
+    // stores of the previous tiles); the gather SDDMM runs at ~3.3e6 nnz*N per us (1.25e6 below 24 columns)
     const double t_g = 12.0 + (double)p->nnz * (double)N / (N < 24 ? 1.25e6 : 3.3e6);
-    const double t_t = 30.0 + (double)(MB * 128) * (double)K / 9.0e5 + 0.4 * t_mma;
+    const double t_t = 30.0 + (double)(MB * 128) * (double)K / 1.7e6 + 0.45 * t_mma;
     return t_t < t_g;
   }
   const double t_tc = 28.0 + std::max(t_stream, t_mma);
@@ -997,7 +997,8 @@ static int plan_backward_A(b200_plan* p, const float* d_G, int64_t ldg, const fl
     }
     if (rc == B200_OK) {
       const int kind = options().tc_kind;
-      const int nt = options().tc_nt > 0 ? options().tc_nt : tc_pick_nt((p->M + 127) / 128, p->K, device_sm_count());
+      const int nt = options().tc_nt > 0 ? options().tc_nt
+                                         : tc_pick_nt_sddmm((p->M + 127) / 128, p->K, (int)N, kind, device_sm_count());
       const size_t need = tc_sddmm_ws_bytes(p->M, p->K, (int)N, nt, kind);
       if (p->sd_ws_bytes < need) {
         if (p->sd_ws) { B200_CUDA_OK(cudaStreamSynchronize(s)); B200_CUDA_OK(cudaFree(p->sd_ws)); p->sd_ws = nullptr; p->sd_ws_bytes = 0; }

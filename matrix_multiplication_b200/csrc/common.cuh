@@ -366,13 +366,14 @@ long long tc_trace_word(int i);
 extern int g_tc_last_kernel, g_tc_pair_capacity;  // diagnostics of the last tensor-core launch (tc_gemm.cu)
 // pattern of a CSR matrix for the tensor-core SDDMM's sampling epilogue
 struct TcSample {
-  int M = 0, K = 0, groups = 0;
+  int M = 0, K = 0, groups = 0, nnz = 0;
   uint32_t* mask = nullptr;  // [groups][M] bit j of (g, m): (m, 32 g + j) is a non-zero
   int* off = nullptr;        // [groups][M] position (in the CSR value array) of the group's first non-zero
 };
 int tc_sample_build(const int* row_ptr, const int* col, int M, int K, int nnz, TcSample* sm, cudaStream_t s);
 void tc_sample_free(TcSample* sm);
 size_t tc_sddmm_ws_bytes(int M, int K, int N, int nt, int kind);
+int tc_pick_nt_sddmm(int MB, int K, int N, int kind, int sms);
 int launch_tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, const float* G, long long ldg,
                     const float* B, long long ldb, int N, bool transposed, float* out, void* ws, size_t ws_bytes,
                     int nt, int kind, cudaStream_t s);

@@ -521,6 +521,7 @@ struct TcParams {
   const int* pair_slot;       // [2][n_pair_tiles]
   int n_pair_tiles, MB2;
   int pair_ptr_ok;            // the pair lists (or the padded SDDMM operand) are in place
+  int dense_pattern;          // SDDMM: the pattern keeps >= 30 % of the cells (tile-shape choice of the short kernel)
 };
 
 // exit protocol: the last CTA to leave re-arms the non-finite flag and the ticket for the next launch
@@ -999,12 +1000,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
 // operand stages; pattern words and scales of the NEXT tile are fetched before the wait for the current one.
 constexpr int SH_EPI_WARPS = 16;
 constexpr int SH_THREADS = (2 + SH_EPI_WARPS) * 32;
-constexpr int SH_NT = 128;
-constexpr int SH_STAGES = 3;
-constexpr int SH_STAGE_BYTES = A_TILE + SH_NT * 256;
-constexpr int SH_BUFS = 512 / SH_NT;
 constexpr int SH_SIDE_BYTES = 32 * 16;  // per warp: (mask, offset, row scale, -) of its 32 rows
-constexpr size_t SH_SMEM = (size_t)SH_STAGES * SH_STAGE_BYTES + 1024 + 256 + (size_t)SH_EPI_WARPS * SH_SIDE_BYTES;
+// NT = pattern rows per tile (the MMA's N): 128 (three 64 KB stages, four TMEM buffers, one group per warp and tile) or
+// 256 (two 96 KB stages, two TMEM buffers, two groups per warp and tile: fewer operand bytes per flop for N > 128)
+template <int NT> struct ShCfg {
+  static constexpr int STAGES = NT == 128 ? 3 : 2;
+  static constexpr int STAGE_BYTES = A_TILE + NT * 256;
+  static constexpr int BUFS = 512 / NT;
+  static constexpr int GPW = NT / 128;  // groups per warp and tile
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)SH_EPI_WARPS * SH_SIDE_BYTES;
+};
 
 struct GroupPre {
   float rs, cs;   // scale of this lane's ROW (lane = row while fetching) / of this lane's COLUMN
@@ -1013,10 +1018,10 @@ struct GroupPre {
 };
 
 // q: which 32 columns of the tile's 128 (TMEM lane quarter), rb: which 32 rows
-template <int KIND>
+template <int KIND, int NT>
 __device__ __forceinline__ GroupPre tc_group_prefetch(const TcParams& p, int tile, int q, int rb, int lane) {
   const int mb = tile / p.NB, nb = tile % p.NB;
-  const int m = mb * BM + rb * 32 + lane;
+  const int m = mb * NT + rb * 32 + lane;
   const int grp = nb * (BM / 32) + q;
   GroupPre t;
   t.rs = 1.f; t.cs = 1.f; t.msk = 0u; t.bs = 0;
@@ -1031,8 +1036,10 @@ __device__ __forceinline__ GroupPre tc_group_prefetch(const TcParams& p, int til
   return t;
 }
 
-template <int KIND>
+template <int KIND, int NT>
 __global__ void __launch_bounds__(SH_THREADS, 1) tc_sddmm_short_kernel(const TcParams p) {
+  constexpr int SH_NT = NT, SH_STAGES = ShCfg<NT>::STAGES, SH_STAGE_BYTES = ShCfg<NT>::STAGE_BYTES;
+  constexpr int SH_BUFS = ShCfg<NT>::BUFS, GPW = ShCfg<NT>::GPW;
   extern __shared__ unsigned char tc_smem_raw[];
   if (*reinterpret_cast<const volatile int*>(p.ctl) != 0) {  // Inf / NaN in a dense operand (uniform over the grid)
     csr_order_sddmm(p.row_ptr, p.col, p.M, p.N, p.G, p.g_sm, p.g_sn, p.B, p.b_sk, p.b_sn, p.C);
@@ -1064,7 +1071,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_sddmm_short_kernel(const TcP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  const int n_tiles = p.MB * p.NB;  // tile = (block of 128 pattern rows mb, block of 128 pattern columns nb)
+  const int n_tiles = p.MB * p.NB;  // tile = (block of NT pattern rows mb, block of 128 pattern columns nb)
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: M operand = 128 packed rows of B (pattern columns), N operand = 128 of G =====
@@ -1131,45 +1138,59 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_sddmm_short_kernel(const TcP
     uint32_t g = 0;
     bool ok = true;
     int tile = blockIdx.x;
-    GroupPre nxt{1.f, 1.f, 0u, 0};
-    if (tile < n_tiles) nxt = tc_group_prefetch<KIND>(p, tile, q, rb, lane);
+    GroupPre nxt[GPW];
+#pragma unroll
+    for (int h = 0; h < GPW; ++h) {
+      nxt[h] = GroupPre{1.f, 1.f, 0u, 0};
+      if (tile < n_tiles) nxt[h] = tc_group_prefetch<KIND, NT>(p, tile, q, rb + 4 * h, lane);
+    }
     for (; tile < n_tiles && ok; tile += gridDim.x, ++g) {
-      const GroupPre cur = nxt;
-      if (tile + (int)gridDim.x < n_tiles) nxt = tc_group_prefetch<KIND>(p, tile + (int)gridDim.x, q, rb, lane);
+      GroupPre cur[GPW];
+#pragma unroll
+      for (int h = 0; h < GPW; ++h) {
+        cur[h] = nxt[h];
+        if (tile + (int)gridDim.x < n_tiles)
+          nxt[h] = tc_group_prefetch<KIND, NT>(p, tile + (int)gridDim.x, q, rb + 4 * h, lane);
+      }
       const uint32_t as = g % SH_BUFS;
       ok = mbar_wait_bounded(acc_full + as, (g / SH_BUFS) & 1u, p.ctl + 1, 400 + (int)as);
       if (!ok) break;
       tc_fence_after();
-      uint32_t v[32];  // v[j] = D^T(column of this lane, row rb * 32 + j)
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * SH_NT + (uint32_t)(rb * 32), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + as);  // the buffer goes back before the stores
-      if (!__any_sync(0xffffffffu, cur.msk != 0u)) continue;  // (also: group beyond K, rows beyond M)
-      side[lane] = make_uint4(cur.msk, (uint32_t)cur.bs, __float_as_uint(cur.rs), 0u);
-      __syncwarp();
-      const float cs = cur.cs;
-      // hand-structured (left to itself the compiler emitted a branch, three scalar LDS and a reload of the output
-      // pointer per row): one broadcast LDS.128 per row, straight-line ALU work, one predicated STG
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        uint32_t mk, bs, sc, pad;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(mk), "=r"(bs), "=r"(sc), "=r"(pad)
-                     : "r"(side_a + (uint32_t)j * 16u));
-        const float x = __uint_as_float(v[j]) * cs * __uint_as_float(sc);
-        const int idx = (int)bs + __popc(mk & lt);
-        asm volatile(
-            "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t.reg .b64 a;\n\t"
-            "and.b32 t, %0, %1;\n\t"
-            "setp.ne.u32 q, t, 0;\n\t"
-            "mad.wide.s32 a, %2, 4, %3;\n\t"
-            "@q st.global.f32 [a], %4;\n\t}"
-            ::"r"(mk), "r"(lbit), "r"(idx), "l"(outp), "f"(x)
-            : "memory");
+      for (int h = 0; h < GPW; ++h) {
+        uint32_t v[32];  // v[j] = D^T(column of this lane, row (rb + 4 h) * 32 + j)
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * SH_NT + (uint32_t)((rb + 4 * h) * 32), v);
+        tmem_ld_wait();
+        if (h == GPW - 1) {  // last read of the buffer: it goes back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + as);
+        }
+        if (!__any_sync(0xffffffffu, cur[h].msk != 0u)) continue;  // (also: group beyond K, rows beyond M)
+        __syncwarp();  // everybody has read `side` before it is overwritten
+        side[lane] = make_uint4(cur[h].msk, (uint32_t)cur[h].bs, __float_as_uint(cur[h].rs), 0u);
+        __syncwarp();
+        const float cs = cur[h].cs;
+        // hand-structured (left to itself the compiler emitted a branch, three scalar LDS and a reload of the output
+        // pointer per row): one broadcast LDS.128 per row, straight-line ALU work, one predicated STG
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          uint32_t mk, bs, sc, pad;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(mk), "=r"(bs), "=r"(sc), "=r"(pad)
+                       : "r"(side_a + (uint32_t)j * 16u));
+          const float x = __uint_as_float(v[j]) * cs * __uint_as_float(sc);
+          const int idx = (int)bs + __popc(mk & lt);
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t.reg .b64 a;\n\t"
+              "and.b32 t, %0, %1;\n\t"
+              "setp.ne.u32 q, t, 0;\n\t"
+              "mad.wide.s32 a, %2, 4, %3;\n\t"
+              "@q st.global.f32 [a], %4;\n\t}"
+              ::"r"(mk), "r"(lbit), "r"(idx), "l"(outp), "f"(x)
+              : "memory");
+        }
       }
-      __syncwarp();  // everybody has read `side` before the next tile overwrites it
     }
   }
   tc_fence_before();
@@ -1618,6 +1639,15 @@ int tc_pick_nt(int MB, int N, int sms) {
   return best;
 }
 
+// SDDMM: tile width the operands are padded for.  When the contraction fits one TMEM accumulation the transposed
+// kernel (tc_sddmm_short_kernel) walks the pattern in blocks of 128 columns, so the padding must be a multiple of 128.
+int tc_pick_nt_sddmm(int MB, int K, int N, int kind, int sms) {
+  const int nt = tc_pick_nt(MB, K, sms);
+  const int KT = (N + bk_of(kind) - 1) / bk_of(kind);
+  if (options().tc_sddmm_short != 0 && KT <= std::max(1, options().tc_chunk)) return nt <= 128 ? 128 : 256;
+  return nt;
+}
+
 // workspace: [control words, 256 B: zero between launches][column maxima, one per padded column][packed B]
 static size_t tc_colmax_bytes(int n_pad) { return (((size_t)n_pad * 4 + 255) / 256) * 256; }
 size_t tc_pack_b_bytes(int K, int N, int nt, int kind) {
@@ -1709,20 +1739,30 @@ static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
   if constexpr (SDDMM) {
     // short contraction: the 16-epilogue-warp kernel over 128 x 128 tiles (the packed operands are laid out in
     // groups of 8 rows, so the tile width is free to differ from the nt they were padded for)
-    if (options().tc_sddmm_short != 0 && p.KT <= p.chunk && (p.terms & ~7) == 0 && p.Nt % SH_NT == 0) {
-      static bool attr_short[64] = {false};
+    // (mode 1: 256-row tiles — fewer operand bytes per flop and per stored entry — unless the contraction is one
+    // k-tile deep AND the pattern is dense, where the 128-row tiles' four TMEM buffers hide the longer store phase
+    // better: measured 0.200 / 0.204 / 0.226 / 0.312 ms (256) vs 0.224 / 0.228 / 0.271 / 0.433 ms (128) at N = 16 / 64 /
+    // 128 / 256 on 16384^2 at 90 % sparsity, 0.261 / 0.257 vs 0.233 / 0.237 ms at 50 % and N <= 64; 2 / 3 force a shape)
+    const int mode = options().tc_sddmm_short;
+    if (mode != 0 && p.KT <= p.chunk && (p.terms & ~7) == 0 && p.Nt % 128 == 0) {
+      const bool wide = mode == 3 || (mode == 1 && p.MB >= 2 && (p.KT > 1 || !p.dense_pattern));
+      p.NB = p.NB * (p.Nt / 128);            // blocks of 128 pattern columns
+      p.Nt = wide ? 256 : 128;
+      if (wide) p.MB = (p.MB + 1) / 2;       // blocks of 256 pattern rows (packed G is padded to an even block count)
+      const int grid = std::max(1, std::min(device_sm_count(), p.MB * p.NB));
+      g_tc_last_kernel = wide ? 4 : 3;
+      static bool attr_short[2][64] = {{false}};
       int dev = 0;
       B200_CUDA_OK(cudaGetDevice(&dev));
-      if (!attr_short[dev & 63]) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tc_sddmm_short_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)SH_SMEM));
-        attr_short[dev & 63] = true;
+      if (!attr_short[wide][dev & 63]) {
+        if (wide) B200_CUDA_OK(cudaFuncSetAttribute(tc_sddmm_short_kernel<KIND, 256>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ShCfg<256>::SMEM));
+        else B200_CUDA_OK(cudaFuncSetAttribute(tc_sddmm_short_kernel<KIND, 128>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ShCfg<128>::SMEM));
+        attr_short[wide][dev & 63] = true;
       }
-      p.NB = p.NB * (p.Nt / SH_NT);
-      p.Nt = SH_NT;
-      const int grid = std::max(1, std::min(device_sm_count(), p.MB * p.NB));
-      g_tc_last_kernel = 3;
-      tc_sddmm_short_kernel<KIND><<<grid, SH_THREADS, SH_SMEM, s>>>(p);
+      if (wide) tc_sddmm_short_kernel<KIND, 256><<<grid, SH_THREADS, ShCfg<256>::SMEM, s>>>(p);
+      else tc_sddmm_short_kernel<KIND, 128><<<grid, SH_THREADS, ShCfg<128>::SMEM, s>>>(p);
       B200_LAUNCH_OK("tc_sddmm_short_kernel");
       return B200_OK;
     }
@@ -1833,7 +1873,7 @@ void tc_sample_free(TcSample* sm) {
 // Pattern of a CSR matrix as per-(32-column group, row) bit masks + value offsets (rows sorted, no duplicates).
 int tc_sample_build(const int* row_ptr, const int* col, int M, int K, int nnz, TcSample* sm, cudaStream_t s) {
   *sm = TcSample{};
-  sm->M = M; sm->K = K;
+  sm->M = M; sm->K = K; sm->nnz = nnz;
   sm->groups = (K + 31) / 32;
   const size_t cells = (size_t)sm->groups * (size_t)std::max(M, 1);
   if (cells * 8 > ((size_t)4 << 30)) {
@@ -1890,6 +1930,7 @@ static int tc_sddmm(const TcSample& sm, const int* row_ptr, const int* col, cons
   p.samp_mask = sm.mask; p.samp_off = sm.off; p.groups = sm.groups;
   p.MB = MB; p.NB = NB; p.Nt = nt;
   p.MB2 = MB2; p.pair_ptr_ok = 1;
+  p.dense_pattern = (double)sm.nnz >= 0.3 * (double)M * (double)K ? 1 : 0;
   p.ctl = ctl;
   p.row_ptr = row_ptr; p.col = col;
   p.G = G; p.g_sm = transposed ? 1 : ldg; p.g_sn = transposed ? ldg : 1;

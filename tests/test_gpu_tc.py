@@ -19,7 +19,8 @@ KINDS = [0, 1]  # 0: tf32 hi + lo, 1: fp16 hi + lo with row / column scaling
 @pytest.fixture(autouse=True)
 def _reset_options():
     yield
-    for k, v in (("tc_kind", capi.TC_KIND_DEFAULT), ("tc_nt", 0), ("tc_chunk", 8), ("tc_terms", 7), ("tc_mode", 1)):
+    for k, v in (("tc_kind", capi.TC_KIND_DEFAULT), ("tc_nt", 0), ("tc_chunk", 8), ("tc_terms", 7), ("tc_mode", 1),
+                 ("tc_sddmm_short", 1)):
         capi.set_option(k, v)
 
 
@@ -257,6 +258,36 @@ def test_tc_sddmm_on_the_pattern(case, kind):
     assert torch.equal(torch.isfinite(o1), torch.isfinite(o2))
     fin = torch.isfinite(o2)
     assert float((o1[fin] - o2[fin]).abs().max()) <= 1e-5 * float(o2[fin].abs().max())
+    plan.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("mode", [2, 3, 0])
+@pytest.mark.parametrize("case", [(1, 33, 40, 1.0), (300, 500, 40, 0.2), (777, 3001, 100, 0.05), (5000, 31, 9, 0.7),
+                                  (1030, 1030, 256, 0.5)])
+def test_tc_sddmm_short_contraction_kernels(case, mode, kind):
+    """Short contractions (one TMEM accumulation): the transposed-product kernel with 128-row tiles (mode 2) and
+    256-row tiles (mode 3), and the general kernel (mode 0), on ragged shapes — same entries, fp64 oracle."""
+    import torch
+    M, K, N, dens = case
+    rng = np.random.default_rng(M * 3 + N)
+    rp, ci, va, _ = random_csr(rng, M, K, dens, heavy_rows=(0,), empty_rows=(1,) if M > 2 else ())
+    G = rng.standard_normal((M, N)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    ref = oracle.sddmm_f64(rp, ci, (M, K), G, B)
+    crow, col, val, Gd, Bd = _dev(rp, ci, va, G, B)
+    capi.set_option("tc_kind", kind)
+    capi.set_option("tc_sddmm_short", mode)
+    plan = capi.Plan(crow, col, val, (M, K))
+    for tr in (False, True):
+        g, b = (Gd.t().contiguous(), Bd.t().contiguous()) if tr else (Gd, Bd)
+        out = plan.backward_A_ex(g, b, torch.full((len(va),), float("nan"), device="cuda:0"),
+                                 flags=OP_FORCE_TC | (OP_B_TRANSPOSED if tr else 0))
+        torch.cuda.synchronize()
+        assert plan.tc_timeout() == 0 and plan.tc_info()["last_path"] == 1
+        short = (N + (63 if kind == 1 else 31)) // (64 if kind == 1 else 32) <= 8
+        assert capi.get_option("tc_last_kernel") == ({2: 3, 3: 4, 0: 1}[mode] if short else 1)
+        assert oracle.rel_err(out.cpu().numpy(), ref) <= TOL
     plan.close()
 
 

@@ -8,6 +8,7 @@ from matrix_multiplication_b200 import capi
 from matrix_multiplication_b200._capi import OP_FORCE_TC
 
 dev = torch.device("cuda")
+MODES = (2, 3, 1, 0)  # 128-row tiles, 256-row tiles, auto, general kernel
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -38,7 +39,7 @@ def case(M, K, N, density, kind=1, time_it=True):
     rows = torch.repeat_interleave(torch.arange(M, device=dev), crow.diff().long())
     ref = (G.double()[rows] * B.double()[col.long()]).sum(1) if val.numel() * N < 4e9 else None
     out = {}
-    for short in (1, 0):
+    for short in MODES:
         capi.set_option("tc_sddmm_short", short)
         dv = torch.full((val.numel(),), float("nan"), device=dev)
         plan.backward_A_ex(G, B, dv, flags=OP_FORCE_TC)
@@ -47,10 +48,11 @@ def case(M, K, N, density, kind=1, time_it=True):
         err = float((dv.double() - ref).abs().max() / ref.abs().max()) if ref is not None else -1.0
         ms = timed(lambda: plan.backward_A_ex(G, B, dv, flags=OP_FORCE_TC)) if time_it else 0.0
         out[short] = (lk, err, ms, plan.tc_timeout(), dv.clone())
-    same = float((out[1][4].double() - out[0][4].double()).abs().max() / out[0][4].double().abs().max())
-    print(f"M {M} K {K} N {N} density {density} kind {kind}: short kernel {out[1][0]} err {out[1][1]:.2e} {out[1][2]:.4f} ms"
-          f" timeout {out[1][3]} | general kernel {out[0][0]} err {out[0][1]:.2e} {out[0][2]:.4f} ms | short vs general {same:.1e}",
-          flush=True)
+    msg = f"M {M} K {K} N {N} density {density} kind {kind}:"
+    for short in MODES:
+        same = float((out[short][4].double() - out[0][4].double()).abs().max() / out[0][4].double().abs().max())
+        msg += f" | mode {short}: kernel {out[short][0]} err {out[short][1]:.2e} vs general {same:.1e} {out[short][2]:.4f} ms timeout {out[short][3]}"
+    print(msg, flush=True)
     capi.set_option("tc_sddmm_short", 1)
     plan.close()
 
@@ -64,7 +66,7 @@ for nt in (128, 256):  # (the 16-warp kernel needs a packing width that is a mul
     case(777, 3001, 100, 0.05, kind=0, time_it=False)
 capi.set_option("tc_nt", 0)
 if not quick:
-    for N in (16, 64, 256):
+    for N in (16, 64, 128, 256):
         for d in (0.1, 0.5):
             case(16384, 16384, N, d)
     case(16384, 16384, 64, 0.1, kind=0)
