@@ -77,7 +77,10 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  *                 paths decides (small or very sparse problems stay on the gather kernels).
  * tc_kind       : split-precision element kind: 0 = tf32 hi + lo, 1 = fp16 hi + lo with per-row / per-column scaling.
  * tc_nt, tc_terms, tc_chunk : tile width override (multiple of 64), which split-precision products are issued (bit mask,
- *                 7 = all), k-tiles accumulated in TMEM between two fp32 register accumulations (accuracy studies). */
+ *                 7 = all), k-tiles accumulated in TMEM between two fp32 register accumulations (accuracy studies).
+ * tc_sddmm_short: tensor-core SDDMM whose contraction fits one TMEM accumulation (N <= tc_chunk k-tiles): 1 = the
+ *                 transposed-product kernel, tile shape chosen by contraction depth and pattern density (default),
+ *                 2 / 3 = that kernel with 128- / 256-row tiles, 0 = the general kernel. */
 int b200_set_option(const char* name, int64_t value);
 int64_t b200_get_option(const char* name);
 

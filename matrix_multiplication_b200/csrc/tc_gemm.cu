@@ -479,6 +479,80 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc(int kind, int nt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// One k-tile's twelve MMAs (4 k-steps x {hi*lo, lo*hi, hi*hi}) with the descriptor arithmetic taken out of the loop.
+// Only the address field of a shared-memory descriptor (bits 0-13, 16-byte units) differs between the operands of a
+// stage, so a descriptor is (lo + small constant, hi): one integer add per operand instead of rebuilding 64 bits.
+// (The timeline of tools/tc_trace.py showed the issuing lane spending 0.67 us per k-tile in the old loop — shifts, ORs,
+// three run-time `terms` branches and a predicate set-up per MMA, ~200 dependent scalar instructions — and a "no MMA,
+// no copies" run of config 5 x 64 still taking 180 of 225 us: the issue loop, not HBM or the tensor pipe, set the pace.)
+// One lane of a converged warp (elect.sync): the compiler then issues the tcgen05 instructions under one predicate
+// instead of wrapping each of them in a loop over the active lanes (ELECT / PLOP3 / BRA.U.ANY per MMA), which is what
+// it emits inside `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <int KIND, bool ACC1>
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (KIND == KIND_F16) {
+    if constexpr (ACC1) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "setp.ne.b32 p, 1, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "setp.ne.b32 p, %5, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
+  } else {
+    if constexpr (ACC1) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "setp.ne.b32 p, 1, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "setp.ne.b32 p, %5, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
+  }
+}
+// sa = shared-window address of the stage's M operand (hi atom of its first 8-row group), the N operand A_TILE behind it;
+// hi and lo atoms 1 KB apart (64 units), a k-step 32 bytes (2 units) along the swizzled row.  Same order of the three
+// products as the general loop (hi*lo, lo*hi, hi*hi), so results are bit-identical to it.
+template <int KIND>
+__device__ __forceinline__ void umma_ktile_all_terms(uint32_t d_tmem, uint32_t sa, uint32_t idesc, uint32_t accumulate) {
+  const uint64_t d0 = umma_desc(sa, ATOM);
+  const uint32_t hi = (uint32_t)(d0 >> 32);
+  const uint32_t a = (uint32_t)d0, b = a + (uint32_t)(A_TILE >> 4);
+  umma_lo<KIND, false>(d_tmem, a, b + 64u, hi, idesc, accumulate);
+  umma_lo<KIND, true>(d_tmem, a + 64u, b, hi, idesc, 1u);
+  umma_lo<KIND, true>(d_tmem, a, b, hi, idesc, 1u);
+#pragma unroll
+  for (uint32_t k = 1; k < 4; ++k) {
+    umma_lo<KIND, true>(d_tmem, a + 2u * k, b + 64u + 2u * k, hi, idesc, 1u);
+    umma_lo<KIND, true>(d_tmem, a + 64u + 2u * k, b + 2u * k, hi, idesc, 1u);
+    umma_lo<KIND, true>(d_tmem, a + 2u * k, b + 2u * k, hi, idesc, 1u);
+  }
+}
+
 struct TcParams {
   const unsigned char* a_tiles;
   const int* blk_ptr;
@@ -846,14 +920,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one lane issues every tcgen05.mma of this CTA =====
-    if (lane == 0) {
+    // ===== MMA issuer: the warp walks the pipeline together, one elected lane issues every tcgen05 instruction =====
+    {
       const uint32_t idesc = umma_idesc(KIND, p.Nt);
+      const bool all_terms = (p.terms & 7) == 7;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;  // chunks issued so far: TMEM buffer g & 1, its barrier phase (g >> 1) & 1
       bool ok = true;
-      const bool tr = (p.terms & 512) && blockIdx.x == 0;
+      const bool tr = (p.terms & 512) && blockIdx.x == 0 && lane == 0;
       int trn = 0;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int mb = tile / p.NB;
@@ -861,7 +936,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
         for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
           const int as = (int)(g & 1u);
           tc_trace(tr, 1, trn, 10);  // MMA lane: starts waiting for a free accumulator
-          ok = mbar_wait_bounded(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as);
+          ok = __all_sync(0xffffffffu, mbar_wait_bounded(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as));
           if (!ok) break;
           tc_trace(tr, 1, trn, 11);  // accumulator free
           tc_fence_after();
@@ -870,24 +945,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
           const int c1 = min(c0 + p.chunk, t1);
           for (int t = c0; t < c1; ++t) {
             tc_trace(tr, 1, trn, 12);  // MMA lane: starts waiting for operands
-            ok = mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage);
+            ok = __all_sync(0xffffffffu, mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage));
             if (!ok) break;
             tc_trace(tr, 1, trn, 13);  // operands landed
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + A_TILE;
+            __syncwarp();
+            if (elect_one()) {
+              if (all_terms) {  // the shipped configuration: straight-line issue, descriptor arithmetic hoisted
+                umma_ktile_all_terms<KIND>(d, sa, idesc, acc);
+              } else {
+                uint32_t a2 = acc;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of every swizzled 128-byte row
-              const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
-              const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
-              if (p.terms & 2) { umma<KIND>(d, a_hi, b_lo, idesc, acc); acc = 1; }
-              if (p.terms & 4) { umma<KIND>(d, a_lo, b_hi, idesc, acc); acc = 1; }
-              if (p.terms & 1) { umma<KIND>(d, a_hi, b_hi, idesc, acc); acc = 1; }
+                for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of every swizzled 128-byte row
+                  const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
+                  const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
+                  if (p.terms & 2) { umma<KIND>(d, a_hi, b_lo, idesc, a2); a2 = 1; }
+                  if (p.terms & 4) { umma<KIND>(d, a_lo, b_hi, idesc, a2); a2 = 1; }
+                  if (p.terms & 1) { umma<KIND>(d, a_hi, b_hi, idesc, a2); a2 = 1; }
+                }
+              }
+              umma_commit(empty + stage);  // the smem slot is free once these MMAs have read it
+              if (t + 1 == c1) umma_commit(acc_full + as);  // partial sums of this chunk complete -> epilogue warps
             }
-            umma_commit(empty + stage);  // the smem slot is free once these MMAs have read it
+            __syncwarp();
+            if (p.terms & 7) acc = 1;
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(acc_full + as);  // partial sums of this chunk complete -> epilogue warps
         }
       }
     }
@@ -1093,37 +1178,48 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_sddmm_short_kernel(const TcP
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer: the whole contraction of a tile goes into one TMEM buffer =====
+    {  // ===== MMA issuer (warp-wide loop, one elected lane issues): a tile's whole contraction goes into one buffer =====
       const uint32_t idesc = umma_idesc(KIND, SH_NT);
+      const bool all_terms = (p.terms & 7) == 7;
       int stage = 0;
       uint32_t phase = 0, g = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++g) {
         const uint32_t as = g % SH_BUFS;
-        ok = mbar_wait_bounded(acc_empty + as, ((g / SH_BUFS) & 1u) ^ 1u, p.ctl + 1, 200 + (int)as);
+        ok = __all_sync(0xffffffffu,
+                        mbar_wait_bounded(acc_empty + as, ((g / SH_BUFS) & 1u) ^ 1u, p.ctl + 1, 200 + (int)as));
         if (!ok) break;
         tc_fence_after();
         const uint32_t d = tmem_base + as * SH_NT;
         uint32_t acc = 0;
         for (int kt = 0; kt < p.KT; ++kt) {
-          ok = mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage);
+          ok = __all_sync(0xffffffffu, mbar_wait_bounded(full + stage, phase, p.ctl + 1, 300 + stage));
           if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * SH_STAGE_BYTES);
           const uint32_t sb = sa + A_TILE;
+          __syncwarp();
+          if (elect_one()) {
+            if (all_terms) {
+              umma_ktile_all_terms<KIND>(d, sa, idesc, acc);
+            } else {
+              uint32_t a2 = acc;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
-            const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
-            if (p.terms & 2) { umma<KIND>(d, a_hi, b_lo, idesc, acc); acc = 1; }
-            if (p.terms & 4) { umma<KIND>(d, a_lo, b_hi, idesc, acc); acc = 1; }
-            if (p.terms & 1) { umma<KIND>(d, a_hi, b_hi, idesc, acc); acc = 1; }
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
+                const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
+                if (p.terms & 2) { umma<KIND>(d, a_hi, b_lo, idesc, a2); a2 = 1; }
+                if (p.terms & 4) { umma<KIND>(d, a_lo, b_hi, idesc, a2); a2 = 1; }
+                if (p.terms & 1) { umma<KIND>(d, a_hi, b_hi, idesc, a2); a2 = 1; }
+              }
+            }
+            umma_commit(empty + stage);
+            if (kt + 1 == p.KT) umma_commit(acc_full + as);
           }
-          umma_commit(empty + stage);
+          __syncwarp();
+          if (p.terms & 7) acc = 1;
           if (++stage == SH_STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (!ok) break;
-        umma_commit(acc_full + as);
       }
     }
   } else {
