@@ -493,63 +493,45 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-template <int KIND, bool ACC1>
+#define B200_UMMA_LO_ASM(CGS, KINDS, PRED_SRC)                                                        \
+  "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                      \
+  "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"                                               \
+  "setp.ne.b32 p, " PRED_SRC ", 0;\n\t"                                                              \
+  "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], da, db, %4, p;\n\t}"
+// CG = cta_group (1: one CTA, M = 128; 2: a CTA pair, M = 256); ACC1: accumulate flag known to be set
+template <int KIND, bool ACC1, int CG>
 __device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                         uint32_t accumulate) {
-  if constexpr (KIND == KIND_F16) {
-    if constexpr (ACC1) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-          "setp.ne.b32 p, 1, 0;\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-          "setp.ne.b32 p, %5, 0;\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-          : "memory");
-    }
-  } else {
-    if constexpr (ACC1) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-          "setp.ne.b32 p, 1, 0;\n\t"
-          "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-          "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-          "setp.ne.b32 p, %5, 0;\n\t"
-          "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-          "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-          : "memory");
-    }
-  }
+#define B200_UMMA_LO_CASE(CGS, KINDS)                                                                               \
+  if constexpr (ACC1)                                                                                               \
+    asm volatile(B200_UMMA_LO_ASM(CGS, KINDS, "1")::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)      \
+                 : "memory");                                                                                       \
+  else                                                                                                              \
+    asm volatile(B200_UMMA_LO_ASM(CGS, KINDS, "%5")::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc),    \
+                 "r"(accumulate)                                                                                    \
+                 : "memory");
+  if constexpr (CG == 1 && KIND == KIND_F16) { B200_UMMA_LO_CASE("1", "f16") }
+  if constexpr (CG == 1 && KIND != KIND_F16) { B200_UMMA_LO_CASE("1", "tf32") }
+  if constexpr (CG == 2 && KIND == KIND_F16) { B200_UMMA_LO_CASE("2", "f16") }
+  if constexpr (CG == 2 && KIND != KIND_F16) { B200_UMMA_LO_CASE("2", "tf32") }
+#undef B200_UMMA_LO_CASE
 }
 // sa = shared-window address of the stage's M operand (hi atom of its first 8-row group), the N operand A_TILE behind it;
 // hi and lo atoms 1 KB apart (64 units), a k-step 32 bytes (2 units) along the swizzled row.  Same order of the three
 // products as the general loop (hi*lo, lo*hi, hi*hi), so results are bit-identical to it.
-template <int KIND>
+template <int KIND, int CG = 1>
 __device__ __forceinline__ void umma_ktile_all_terms(uint32_t d_tmem, uint32_t sa, uint32_t idesc, uint32_t accumulate) {
   const uint64_t d0 = umma_desc(sa, ATOM);
   const uint32_t hi = (uint32_t)(d0 >> 32);
   const uint32_t a = (uint32_t)d0, b = a + (uint32_t)(A_TILE >> 4);
-  umma_lo<KIND, false>(d_tmem, a, b + 64u, hi, idesc, accumulate);
-  umma_lo<KIND, true>(d_tmem, a + 64u, b, hi, idesc, 1u);
-  umma_lo<KIND, true>(d_tmem, a, b, hi, idesc, 1u);
+  umma_lo<KIND, false, CG>(d_tmem, a, b + 64u, hi, idesc, accumulate);
+  umma_lo<KIND, true, CG>(d_tmem, a + 64u, b, hi, idesc, 1u);
+  umma_lo<KIND, true, CG>(d_tmem, a, b, hi, idesc, 1u);
 #pragma unroll
   for (uint32_t k = 1; k < 4; ++k) {
-    umma_lo<KIND, true>(d_tmem, a + 2u * k, b + 64u + 2u * k, hi, idesc, 1u);
-    umma_lo<KIND, true>(d_tmem, a + 64u + 2u * k, b + 2u * k, hi, idesc, 1u);
-    umma_lo<KIND, true>(d_tmem, a + 2u * k, b + 2u * k, hi, idesc, 1u);
+    umma_lo<KIND, true, CG>(d_tmem, a + 2u * k, b + 64u + 2u * k, hi, idesc, 1u);
+    umma_lo<KIND, true, CG>(d_tmem, a + 64u + 2u * k, b + 2u * k, hi, idesc, 1u);
+    umma_lo<KIND, true, CG>(d_tmem, a + 2u * k, b + 2u * k, hi, idesc, 1u);
   }
 }
 
@@ -954,7 +936,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_spmm_kernel(const TcParams p
             __syncwarp();
             if (elect_one()) {
               if (all_terms) {  // the shipped configuration: straight-line issue, descriptor arithmetic hoisted
-                umma_ktile_all_terms<KIND>(d, sa, idesc, acc);
+                umma_ktile_all_terms<KIND, 1>(d, sa, idesc, acc);
               } else {
                 uint32_t a2 = acc;
 #pragma unroll
@@ -1201,7 +1183,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_sddmm_short_kernel(const TcP
           __syncwarp();
           if (elect_one()) {
             if (all_terms) {
-              umma_ktile_all_terms<KIND>(d, sa, idesc, acc);
+              umma_ktile_all_terms<KIND, 1>(d, sa, idesc, acc);
             } else {
               uint32_t a2 = acc;
 #pragma unroll
@@ -1477,10 +1459,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_sp
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
-    } else if (lane == 0) {
-      // ===== MMA issuer (leader CTA): one lane issues every tcgen05.mma of the pair =====
+    } else if (rank == 0) {
+      // ===== MMA issuer (leader CTA): the warp walks the pipeline, one elected lane issues every tcgen05 instruction =====
       const uint32_t idesc = (1u << 4) | ((KIND == KIND_F16 ? 0u : 2u) << 7) | ((KIND == KIND_F16 ? 0u : 2u) << 10) |
                              ((uint32_t)(p.Nt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const bool all_terms = (p.terms & 7) == 7;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;
@@ -1490,30 +1473,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_sp
         const int t0 = SDDMM ? 0 : __ldg(p.pair_ptr + mp), t1 = SDDMM ? p.KT : __ldg(p.pair_ptr + mp + 1);
         for (int c0 = t0; c0 < t1 && ok; c0 += p.chunk, ++g) {
           const int as = (int)(g & 1u);
-          ok = mbar_wait_cluster(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as);
+          ok = __all_sync(0xffffffffu, mbar_wait_cluster(acc_empty + as, ((g >> 1) & 1u) ^ 1u, p.ctl + 1, 200 + as));
           if (!ok) break;
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(as * p.Nt);
           uint32_t acc = 0;
           const int c1 = min(c0 + p.chunk, t1);
           for (int t = c0; t < c1; ++t) {
-            ok = mbar_wait_cluster(full + stage, phase, p.ctl + 1, 300 + stage);
+            ok = __all_sync(0xffffffffu, mbar_wait_cluster(full + stage, phase, p.ctl + 1, 300 + stage));
             if (!ok) break;
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + A_TILE;
+            __syncwarp();
+            if (elect_one()) {
+              if (all_terms) {
+                umma_ktile_all_terms<KIND, 2>(d, sa, idesc, acc);
+              } else {
+                uint32_t a2 = acc;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
-              const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
-              if (p.terms & 2) { umma2<KIND>(d, a_hi, b_lo, idesc, acc); acc = 1; }
-              if (p.terms & 4) { umma2<KIND>(d, a_lo, b_hi, idesc, acc); acc = 1; }
-              if (p.terms & 1) { umma2<KIND>(d, a_hi, b_hi, idesc, acc); acc = 1; }
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t a_hi = umma_desc(sa + k * 32, ATOM), a_lo = umma_desc(sa + 1024 + k * 32, ATOM);
+                  const uint64_t b_hi = umma_desc(sb + k * 32, ATOM), b_lo = umma_desc(sb + 1024 + k * 32, ATOM);
+                  if (p.terms & 2) { umma2<KIND>(d, a_hi, b_lo, idesc, a2); a2 = 1; }
+                  if (p.terms & 4) { umma2<KIND>(d, a_lo, b_hi, idesc, a2); a2 = 1; }
+                  if (p.terms & 1) { umma2<KIND>(d, a_hi, b_hi, idesc, a2); a2 = 1; }
+                }
+              }
+              umma_commit2(empty + stage);  // frees the slot in both CTAs
+              if (t + 1 == c1) umma_commit2(acc_full + as);  // both CTAs' epilogue warps
             }
-            umma_commit2(empty + stage);  // frees the slot in both CTAs
+            __syncwarp();
+            if (p.terms & 7) acc = 1;
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit2(acc_full + as);  // both CTAs' epilogue warps
         }
       }
     }

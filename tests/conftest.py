@@ -31,6 +31,20 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _engine_options_from_env():
+    """B200_TEST_OPTS="name=value,..." runs the suite with engine options set (e.g. tc_pair=1: the CTA-pair
+    tensor-core kernel behind every tile test).  Unset: nothing happens."""
+    import os
+    opts = os.environ.get("B200_TEST_OPTS", "")
+    if opts and _has_gpu():
+        from matrix_multiplication_b200 import capi
+        for kv in opts.split(","):
+            k, v = kv.split("=")
+            capi.set_option(k.strip(), int(v))
+    yield
+
+
 def load_golden(name):
     with np.load(GOLDEN / f"{name}.npz") as z:
         return {k: z[k] for k in z.files}
