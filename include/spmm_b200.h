@@ -78,6 +78,8 @@ int b200_smoke_kernel(void* stream, int* sm_count);
  * tc_kind       : split-precision element kind: 0 = tf32 hi + lo, 1 = fp16 hi + lo with per-row / per-column scaling.
  * tc_nt, tc_terms, tc_chunk : tile width override (multiple of 64), which split-precision products are issued (bit mask,
  *                 7 = all), k-tiles accumulated in TMEM between two fp32 register accumulations (accuracy studies).
+ * tc_pair       : CTA pairs (tcgen05 cta_group::2) for the tiles: 0 never, 1 whenever the shape allows it, 2 auto (default:
+ *                 256-wide tiles on a long contraction).
  * tc_sddmm_short: tensor-core SDDMM whose contraction fits one TMEM accumulation (N <= tc_chunk k-tiles): 1 = the
  *                 transposed-product kernel, tile shape chosen by contraction depth and pattern density (default),
  *                 2 / 3 = that kernel with 128- / 256-row tiles, 0 = the general kernel. */

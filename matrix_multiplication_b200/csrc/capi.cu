@@ -321,7 +321,7 @@ int b200_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_trace_idx")) { g_trace_idx = (int)value; return B200_OK; }
   if (!strcmp(name, "tc_chunk")) { options().tc_chunk = (int)std::max<int64_t>(1, value); return B200_OK; }
   if (!strcmp(name, "tc_kind")) { options().tc_kind = value ? 1 : 0; return B200_OK; }
-  if (!strcmp(name, "tc_pair")) { options().tc_pair = value ? 1 : 0; return B200_OK; }
+  if (!strcmp(name, "tc_pair")) { options().tc_pair = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)); return B200_OK; }
   if (!strcmp(name, "tc_sddmm_short")) { options().tc_sddmm_short = (int)(value & 3); return B200_OK; }
   if (!strcmp(name, "tc_min_density_pct")) { options().tc_min_density_pct = (int)value; return B200_OK; }
   set_error("unknown option '%s'", name);

@@ -64,7 +64,7 @@ struct Options {
   int tc_nt = 0;           // tile width override (multiple of 32, <= 256); 0 = auto
   int tc_terms = 7;        // which split-precision products are issued: 1 hi*hi, 2 hi*lo, 4 lo*hi
   int tc_chunk = 8;        // k-tiles accumulated in TMEM between two fp32 register accumulations (<= 96 truncating adds)
-  int tc_pair = 0;         // 1 = CTA pairs (cta_group::2: tc_spmm2_kernel), 0 = one CTA per tile (default: measured equal, profiles/r2_tc_breakdown.md)
+  int tc_pair = 2;         // CTA pairs (cta_group::2: tc_spmm2_kernel): 0 = never, 1 = whenever the shape allows it, 2 = auto (256-wide tiles on a long contraction: measured 10 % faster there, slower elsewhere; profiles/r2_experiments.md)
   int tc_sddmm_short = 1;  // tensor-core SDDMM whose contraction fits one TMEM accumulation: 1 = the 16-epilogue-warp kernel (tc_sddmm_short_kernel), 0 = the general kernel
   int tc_kind = 1;         // 0 = tf32 hi/lo split, 1 = fp16 hi/lo split with row / column scaling (default)
   int tc_min_density_pct = 2;  // auto rule: never below this density (percent of M*K); above it a cost model decides

@@ -1856,8 +1856,14 @@ static int tc_run(TcParams& p, int tiles, cudaStream_t s) {
       return B200_OK;
     }
   }
-  // CTA pairs (cta_group::2) when there are at least two row blocks: each CTA stages A + half of the B tile
-  if (options().tc_pair != 0 && p.MB >= 2 && p.pair_ptr_ok) {
+  // CTA pairs (cta_group::2) when there are at least two row blocks: each CTA stages A + half of the B tile.
+  // tc_pair = 2 (default, auto): only where they were measured faster — 256-wide tiles on a long contraction, where one
+  // CTA's operand stream (96 KB per k-tile) runs into the L2 -> SM rate of its SM and only two stages fit: config 5
+  // x 256 0.375 / 0.363 -> 0.339 / 0.331 ms at 50 / 90 % sparsity; narrower tiles and config 3's short K are slower
+  // on pairs (profiles/r2_experiments.md).
+  const int pair_mode = options().tc_pair;
+  const bool want_pair = pair_mode == 1 || (pair_mode == 2 && !SDDMM && p.Nt == 256 && p.KT >= 128);
+  if (want_pair && p.MB >= 2 && p.pair_ptr_ok) {
     const int stage2 = A_TILE + p.Nt * 128;
     p.stages = std::min(MAX_STAGES, (int)((TC_SMEM_MAX - 1024 - 256 - STG_BYTES) / stage2));
     const size_t smem2 = (size_t)p.stages * stage2 + 1024 + 256 + STG_BYTES;
@@ -1905,7 +1911,7 @@ static int tc_launch(const TcStore& st, const int* row_ptr, const int* col, cons
   p.b_pack = b_pack; p.NG = NG;
   p.C = C; p.ldc = ldc; p.M = st.M; p.N = N; p.bias = bias; p.flags = flags;
   p.row_scale = st.row_scale; p.colmax = colmax;
-  p.MB = st.MB; p.NB = NB; p.Nt = nt;
+  p.MB = st.MB; p.NB = NB; p.Nt = nt; p.KT = st.KT;  // (KT: only read by the kernel-shape choice in tc_run)
   p.pair_ptr = st.pair_ptr; p.pair_kt = st.pair_kt; p.pair_slot = st.pair_slot;
   p.n_pair_tiles = std::max(st.n_pair_tiles, 1); p.MB2 = st.MB2; p.pair_ptr_ok = st.pair_ptr != nullptr;
   p.ctl = ctl;

@@ -20,7 +20,7 @@ KINDS = [0, 1]  # 0: tf32 hi + lo, 1: fp16 hi + lo with row / column scaling
 def _reset_options():
     yield
     for k, v in (("tc_kind", capi.TC_KIND_DEFAULT), ("tc_nt", 0), ("tc_chunk", 8), ("tc_terms", 7), ("tc_mode", 1),
-                 ("tc_sddmm_short", 1)):
+                 ("tc_sddmm_short", 1), ("tc_pair", 2)):
         capi.set_option(k, v)
 
 
@@ -290,6 +290,28 @@ def test_tc_sddmm_short_contraction_kernels(case, mode, kind):
         assert capi.get_option("tc_last_kernel") in want
         assert oracle.rel_err(out.cpu().numpy(), ref) <= TOL
     plan.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("case", [(129, 33, 65, 0.3, (0,), (128,)), (300, 200, 100, 0.3, (5,), (0, 299)),
+                                  (513, 777, 257, 0.05, (100,), (511, 512)), (1000, 1000, 777, 0.1, (), ())])
+def test_tc_cta_pair_kernel(case, kind):
+    """The cta_group::2 form of the tile kernel (two CTAs of a cluster share every B tile; the default for 256-wide
+    tiles on long contractions) forced on small ragged operands: forward, transposed operands, bias + ReLU."""
+    M, K, N, dens, heavy, empty = case
+    rng = np.random.default_rng(M + K)
+    rp, ci, va, _ = random_csr(rng, M, K, dens, heavy_rows=heavy, empty_rows=empty)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal(M).astype(np.float32)
+    capi.set_option("tc_kind", kind)
+    capi.set_option("tc_pair", 1)
+    ref = oracle.spmm_f64(rp, ci, va, (M, K), B)
+    C, info = _forward(rp, ci, va, (M, K), B)
+    assert info["last_path"] == 1 and capi.get_option("tc_last_kernel") == 2
+    assert oracle.rel_err(C, ref) <= TOL
+    Ct, _ = _forward(rp, ci, va, (M, K), B, bias=bias, bt=True, ct=True, flags=OP_FORCE_TC | OP_RELU)
+    assert capi.get_option("tc_last_kernel") == 2
+    assert oracle.rel_err(Ct, np.maximum(ref + bias[:, None], 0.0)) <= TOL
 
 
 def test_tc_auto_rule_picks_paths():
