@@ -40,6 +40,14 @@ def test_argument_validation():
     capi.set_option("items_per_task", 64)
     assert capi.get_option("items_per_task") == 64
     capi.set_option("items_per_task", 0)
+    # kernel-shape options of the tile path: defaults (auto) and clamping
+    assert capi.get_option("tc_pair") == 2 and capi.get_option("tc_sddmm_short") == 1
+    for name, values in (("tc_pair", (0, 1, 2)), ("tc_sddmm_short", (0, 2, 3, 1))):
+        for v in values:
+            capi.set_option(name, v)
+            assert capi.get_option(name) == v
+    capi.set_option("tc_pair", 7)
+    assert capi.get_option("tc_pair") == 2
     assert L.b200_spmm_workspace_bytes(1000, 5000, 128) >= 256 + 2 * ((6000 + 127) // 128) * 128 * 4
 
 
