@@ -664,9 +664,10 @@ static int plan_spmm(b200_plan* p, int side, const int* row_ptr, const int* col,
 // Should this product run on the block-dense tensor-core path?  ("crossover rule")
 // Auto mode compares two measured cost models (B200, profiles/r2_tc_crossover.md):
 //   gather kernels : 12 us + nnz * N / 5.0e6 us   (one gathered B element per FMA; ~2e6 per us below 24 columns)
-//   tensor tiles   : 28 us + max(streaming the densified tiles, the MMAs):
+//   tensor tiles   : 28 us + max(streaming the densified tiles, the MMAs, a CTA's serial walk over its k-tiles):
 //                      tile bytes (x column blocks when they exceed L2) / 5.5e6 B per us,
-//                      6 * M_pad * K * N_pad / R, R = 1.3e9 (fp16 split) or 0.65e9 (tf32 split) flop per us
+//                      6 * M_pad * K * N_pad / R, R = 1.3e9 (fp16 split) or 0.65e9 (tf32 split) flop per us,
+//                      waves * k-tiles * (0.4 + 0.8 Nt / 256) us
 // so small problems stay on the gather kernels (launch-bound: config 1-2), and large ones switch at ~4-5 % density.
 static double g_last_tc_estimate_us = 0.0;  // the tiles' estimated time of the last plan_wants_tc() call (same thread)
 static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t flags, bool sddmm = false) {
@@ -699,7 +700,15 @@ static bool plan_wants_tc(const b200_plan* p, int M, int K, int64_t N, uint32_t 
     const double t_t = 30.0 + (double)(MB * 128) * (double)K / 1.7e6 + 0.45 * t_mma;
     return t_t < t_g;
   }
-  const double t_tc = 28.0 + std::max(t_stream, t_mma);
+  // a CTA walks the k-tiles of its tiles one after the other: ~0.4 us of stage round trip per k-tile (after the
+  // stages that fit have been divided in) + the 12 MMAs (0.8 us at Nt = 256), times the tiles a CTA gets
+  // (tools/tc_stream_probe.py; config 3 fc1: 3 waves x 12 x 1.2 = 43 us, config 5 x 256: 256 x 1.2 = 307 us)
+  const int sms = device_sm_count();
+  const int nt = options().tc_nt > 0 ? options().tc_nt : tc_pick_nt((int)MB, (int)std::min<int64_t>(N, 1 << 20), sms);
+  const double waves = std::ceil((double)MB * (double)((N + nt - 1) / nt) / (double)std::max(1, sms));
+  const double k_tiles = (double)((K + (f16 ? 63 : 31)) / (f16 ? 64 : 32));
+  const double t_chain = waves * k_tiles * (0.4 + 0.8 * (double)nt / 256.0);
+  const double t_tc = 28.0 + std::max(std::max(t_stream, t_mma), t_chain);
   g_last_tc_estimate_us = t_tc;
   return t_tc < t_gather;
 }
