@@ -2,14 +2,17 @@ import sys, time; sys.path.insert(0, '.')
 import numpy as np, torch
 from matrix_multiplication_b200 import capi, synthetic
 z = np.load('/tmp/b200_bench_cache/c4_None.npz', allow_pickle=True) if False else None
-rp, ci, va, (M, K) = synthetic.rmat_csr(18, 16, seed=0)
+rp, ci, va, (M, K) = synthetic.rmat_csr(int(sys.argv[1]) if len(sys.argv) > 1 else 18, 16, seed=0)
 N = 128
 dev = torch.device('cuda:0')
 crow, col, val = (torch.from_numpy(x).to(dev) for x in (rp, ci, va))
 plan = capi.Plan(crow, col, val, (M, K))
 B = torch.rand(K, N).pin_memory(); C = torch.empty(M, N).pin_memory()
-for panels in (1, 2, 4, 8, 16):
+ref = None
+for panels in (1, 2, 3, 4, 8, 16):
     for _ in range(2): plan.forward_host(B, C, panels)
+    if ref is None: ref = C.clone()
+    else: assert torch.equal(ref, C), f"panels={panels}: result differs from the single-panel run"
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(5): plan.forward_host(B, C, panels)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5 * 1e3
